@@ -1,0 +1,132 @@
+/*
+ * tvidz_b200.h -- C ABI of the B200-native TVIDZ analysis hot path.
+ *
+ * The reference (infraheads/tvidz) has no FFI: its seams for this path are a
+ * Python function (inspector/db.py:76 find_duplicates) and a subprocess text
+ * protocol (inspector/app.py:202-232, the ffmpeg `select=gt(scene\,0.3),showinfo`
+ * pipeline).  These entry points are what a ctypes binding inside the inspector
+ * would call instead; INTEGRATION.md shows that binding.
+ *
+ * Conventions: every function returns 0 on success and a negative tvz_status on
+ * failure; tvz_last_error() returns a thread-local message.  Nothing throws,
+ * nothing frees caller memory.  Pointers prefixed d_ are device pointers on the
+ * current CUDA device, h_ are host pointers.  `stream` is a cudaStream_t passed
+ * as void* (NULL = default stream).  All calls are re-entrant; a tvz_catalog may
+ * be matched from several host threads at once provided each thread passes its
+ * own tvz_match_ws (the reference runs one analysis thread per upload,
+ * app.py:43,472).
+ */
+#ifndef TVIDZ_B200_H
+#define TVIDZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tvz_status {
+    TVZ_OK = 0,
+    TVZ_ERR_INVALID = -1,   /* bad argument */
+    TVZ_ERR_CUDA = -2,      /* CUDA runtime error; see tvz_last_error() */
+    TVZ_ERR_NOMEM = -3,
+    TVZ_ERR_OVERFLOW = -4   /* result did not fit the caller's capacity; *n_out holds the size needed */
+} tvz_status;
+
+const char *tvz_last_error(void);
+int tvz_abi_version(void);
+
+/* ------------------------------------------------------------------ stage 1
+ * Replaces the arithmetic of FFmpeg's `select` scene detector that the
+ * reference launches at inspector/app.py:202-209.
+ */
+
+/* Luma byte-SAD between consecutive frames (FFmpeg scene_sad.c ff_scene_sad_c,
+ * invoked per frame by f_select.c get_scene_score; call site app.py:206).
+ *   d_luma : 8-bit luma, frame t of stream s at
+ *            d_luma + s*stream_stride_bytes + t*frame_stride_bytes, rows
+ *            pitch_bytes apart, `width` visible bytes per row.
+ *   d_sad  : uint64 [n_streams][n_frames]; d_sad[s][0] = 0 and d_sad[s][t] is
+ *            the SAD of frames t-1 and t.  Exact integers.
+ * Layouts whose base, pitch and strides are 16-byte multiples (with pitch ==
+ * width, or width % 16 == 0) take the TMA bulk-copy kernel; anything else takes
+ * a slower generic CUDA kernel.  There is no CPU path.
+ */
+int tvz_sad_luma_u8(const uint8_t *d_luma, int n_streams, int n_frames, int width, int height,
+                    int64_t pitch_bytes, int64_t frame_stride_bytes, int64_t stream_stride_bytes,
+                    uint64_t *d_sad, void *stream);
+
+/* Which kernel tvz_sad_luma_u8 would pick for this layout: 1 = TMA bulk, 0 = generic. */
+int tvz_sad_luma_u8_path(const uint8_t *d_luma, int width, int height, int64_t pitch_bytes,
+                         int64_t frame_stride_bytes, int64_t stream_stride_bytes);
+
+/* Scene score and selection (f_select.c get_scene_score + select_frame with
+ * expression gt(scene,threshold); libavutil av_clipf float rounding included):
+ *   mafd = (double)sad/(w*h)/2^(bitdepth-8); diff = |mafd - prev_mafd|;
+ *   score = (double)(float)clip(min(mafd,diff)/100, 0, 1); frame 0 scores 0.
+ *   selected = score > threshold.
+ * d_score / d_selected may be NULL.
+ */
+int tvz_scene_select(const uint64_t *d_sad, int n_streams, int n_frames, int width, int height,
+                     int bitdepth, double threshold, double *d_score, uint8_t *d_selected,
+                     void *stream);
+
+/* End-to-end entry with HOST buffers: the call a binding makes when decoded
+ * frames sit in (ideally pinned) host memory.  Frames are streamed to the device
+ * in chunks over two copy/compute streams, scored, and the three result arrays
+ * [n_streams][n_frames] are written back to host memory.  Any of h_sad, h_score,
+ * h_selected may be NULL.  chunk_frames <= 0 picks a default.
+ */
+int tvz_scene_score_host(const uint8_t *h_luma, int n_streams, int n_frames, int width, int height,
+                         int64_t pitch_bytes, int64_t frame_stride_bytes, int64_t stream_stride_bytes,
+                         int bitdepth, double threshold, int chunk_frames,
+                         uint64_t *h_sad, double *h_score, uint8_t *h_selected);
+
+/* ------------------------------------------------------------------ stage 2
+ * Replaces inspector/db.py:76-94 find_duplicates over the rows of
+ * `video_timestamps` (db.py:22-27: one float8[] per video).
+ */
+typedef struct tvz_catalog tvz_catalog;     /* device-resident packed catalogue (one shard) */
+typedef struct tvz_match_ws tvz_match_ws;   /* per-thread query workspace */
+
+/* Pack rows (CSR: h_ts[h_off[r] .. h_off[r+1]) is row r, h_video_id[r] its
+ * videos.id) onto the current device.  Stored values are canonicalised so that
+ * bitwise equality equals Python float `==` (db.py:88): -0.0 -> +0.0, NaNs
+ * dropped, repeats inside a row dropped (they never change a match count). */
+int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_video_id,
+                       int64_t n_rows, tvz_catalog **out);
+void tvz_catalog_destroy(tvz_catalog *cat);
+int64_t tvz_catalog_rows(const tvz_catalog *cat);
+int64_t tvz_catalog_values(const tvz_catalog *cat);     /* stored doubles after canonicalisation */
+int64_t tvz_catalog_algo_bytes(const tvz_catalog *cat); /* 8*values + 8*(rows+1), SURVEY.md 8d */
+
+int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_ws **out);
+void tvz_match_ws_destroy(tvz_match_ws *ws);
+
+/* find_duplicates(new_timestamps=q[0..qn), min_match): every row whose
+ * match_count = #{i : q[i] in row} is >= min_match, in catalogue order.
+ * Host-buffer call: q and the outputs are host memory; the call returns after
+ * the results are on the host.  out_kth (nullable) receives, per hit, the
+ * 1-based query index at which the row reached min_match (0 if min_match <= 0):
+ * the step at which the per-cut loop of app.py:231-255 first reports it. */
+int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q, int qn, int min_match,
+                      int32_t *out_video_id, int32_t *out_count, int32_t *out_kth,
+                      int64_t cap, int64_t *n_out);
+
+/* Device-resident variant for pipelines, CUDA graphs and the sharded matcher:
+ * enqueues the query upload, the count kernel and the ordered compaction on
+ * `stream` and returns without synchronising.  Results stay on the device:
+ *   tvz_match_ws_hits():  int32 [hit_capacity][2] = (video_id, match_count)
+ *   tvz_match_ws_nhits(): int64, the number of qualifying rows (may exceed capacity;
+ *                         only the first hit_capacity are stored)
+ */
+int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn,
+                            int min_match, void *stream);
+const int32_t *tvz_match_ws_hits(const tvz_match_ws *ws);
+const int64_t *tvz_match_ws_nhits(const tvz_match_ws *ws);
+const int32_t *tvz_match_ws_counts(const tvz_match_ws *ws);  /* int32 [rows] scratch (zero between calls) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVIDZ_B200_H */

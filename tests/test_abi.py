@@ -1,0 +1,62 @@
+"""The C-ABI library loads and exports every symbol include/tvidz_b200.h declares
+(no compute calls here: this file runs without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import tvidz_b200._lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    with open(os.path.join(ROOT, "include", "tvidz_b200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(tvz_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_bound_and_exported():
+    names = _declared()
+    assert len(names) >= 15
+    lib = ctypes.CDLL(L.LIB_PATH)
+    bound = {n for n, _, _ in L.SYMBOLS}
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in bound, f"{n} declared in the header but not bound in _lib.py"
+    assert bound <= set(names), "binding names a symbol the header does not declare"
+
+
+def test_abi_version_and_error_string():
+    lib = L.lib()
+    assert lib.tvz_abi_version() == 1
+    assert isinstance(lib.tvz_last_error(), bytes)
+
+
+def test_argument_validation_needs_no_gpu():
+    lib = L.lib()
+    rc = lib.tvz_sad_luma_u8(None, 1, 2, 16, 16, 16, 256, 512, None, None)
+    assert rc == -1 and b"null" in lib.tvz_last_error()
+    rc = lib.tvz_sad_luma_u8(1, 1, 2, 16, 16, 8, 256, 512, 1, None)
+    assert rc == -1 and b"pitch" in lib.tvz_last_error()
+    with pytest.raises(L.TvzError):
+        L.check(rc)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libtvidz_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        L.lib()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "tvidz_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+                assert "oracle/" not in src and "tvzo_" not in src, fn

@@ -1,0 +1,118 @@
+"""The CPU oracle for stage 1 against the known-answer tests of SURVEY.md A.5
+(parity unpinned: no FFmpeg vector exists in the reference) and the host-side
+timestamp text protocol against the oracle's independent C restatement."""
+import numpy as np
+import pytest
+
+import oracle
+from tvidz_b200 import scene
+
+W, H = 1920, 1080
+
+
+def _const(v, n=1):
+    return np.full((n, H, W), v, np.uint8)
+
+
+def _run(frames, width=None, threshold=0.3):
+    sad, score, sel, _ = oracle.scene_batch(np.ascontiguousarray(frames[None]), width, threshold)
+    return sad[0], score[0], sel[0]
+
+
+def test_identical_frames_score_zero():                      # A.5 #1
+    sad, score, sel = _run(np.concatenate([_const(77, 4)]))
+    assert sad.tolist() == [0, 0, 0, 0] and not score.any() and not sel.any()
+
+
+def test_black_to_white_max_sad():                           # A.5 #2
+    sad, score, sel = _run(np.concatenate([_const(0), _const(255), _const(255)]))
+    assert sad.tolist() == [0, 528768000, 0]
+    assert score.tolist() == [0.0, 1.0, 0.0] and sel.tolist() == [0, 1, 0]
+
+
+def test_float_cast_edge_exactly_point_three():              # A.5 #3
+    sad, score, sel = _run(np.concatenate([_const(0), _const(30)]))
+    assert sad[1] == 62208000
+    assert score[1] == float(np.float32(0.3)) and score[1] > 0.3 and sel[1] == 1
+    # one count less: 0.29999999518 -> float32 0.29999998 -> not selected
+    sc, se = oracle.scene_scores(np.array([0, 62207999], np.uint64), W, H)
+    assert sc[1] == float(np.float32(62207999 / (W * H) / 100.0)) and sc[1] < 0.3 and se[1] == 0
+
+
+def test_fade_fires_once():                                  # A.5 #4
+    frames = np.concatenate([_const(40 * k) for k in range(6)])
+    sad, score, sel = _run(frames)
+    assert sel.tolist() == [0, 1, 0, 0, 0, 0]
+    assert score[1] == float(np.float32(0.4)) and not score[2:].any()
+
+
+def test_padding_never_contributes():                        # A.5 #5
+    rng = np.random.default_rng(5)
+    w, p, h = 1918, 1984, 37
+    a = rng.integers(0, 256, (3, h, p), dtype=np.uint8)
+    b = a.copy()
+    b[:, :, w:] = rng.integers(0, 256, (3, h, p - w), dtype=np.uint8)   # different padding only
+    s1, _, _ = _run(a, width=w)
+    s2, _, _ = _run(b, width=w)
+    ref = [0] + [int(np.abs(a[t, :, :w].astype(np.int64) - a[t - 1, :, :w]).sum()) for t in (1, 2)]
+    assert s1.tolist() == ref == s2.tolist()
+
+
+@pytest.mark.parametrize("n,text", [(37, "1.23333"), (3037, "101.233"), (215999, "7199.97"), (300000, "10000"),
+                                    (0, "0"), (1, "0.0333333"), (30, "1")])
+def test_pts_time_text_g6(n, text):                          # A.5 #6
+    assert oracle.pts_time_string(n, 1, 30, 0) == text
+    assert scene.pts_time_string(n, (1, 30), "g6") == text
+
+
+@pytest.mark.parametrize("n,text", [(37, "1.233333"), (3037, "101.233333"), (215999, "7199.966667"),
+                                    (300000, "10000"), (0, "0"), (1, "0.0333333"), (30, "1")])
+def test_pts_time_text_f7(n, text):
+    assert oracle.pts_time_string(n, 1, 30, 1) == text
+    assert scene.pts_time_string(n, (1, 30), "f7") == text
+
+
+def test_uint32_headroom():                                  # A.5 #7
+    assert 255 * 3840 * 2160 == 2115072000 < 2**32 < 255 * 7680 * 4320
+
+
+@pytest.mark.parametrize("tb", [(1, 30), (1, 15360), (1001, 30000), (1, 25)])
+@pytest.mark.parametrize("fmt,mode", [("g6", 0), ("f7", 1)])
+def test_text_protocol_python_equals_c(tb, fmt, mode):
+    rng = np.random.default_rng(11)
+    pts = np.sort(rng.integers(0, 40_000_000, 4000))
+    for p in pts[::7]:
+        assert scene.pts_time_string(int(p), tb, fmt) == oracle.pts_time_string(int(p), tb[0], tb[1], mode)
+    sel = (rng.random(pts.shape[0]) < 0.3).astype(np.uint8)
+    pts[10] = pts[9]                                          # a repeated pts -> consecutive dedup
+    sel[9] = sel[10] = 1
+    got = scene.cut_timestamps(sel, pts, tb, fmt)
+    want = oracle.cut_timestamps(sel, tb[0], tb[1], mode, pts)
+    assert got == want and len(got) < int(sel.sum())
+
+
+def test_showinfo_shim_round_trips_through_reference_parse():
+    sel = np.zeros(400, np.uint8)
+    sel[[37, 38, 120, 399]] = 1
+    cuts = []
+    for line in scene.showinfo_lines(sel):
+        line = line.strip()                                   # the parse of app.py:216-232
+        assert 'showinfo' in line and 'pts_time:' in line
+        ts = float(line.split('pts_time:')[1].split()[0])
+        if not cuts or ts != cuts[-1]:
+            cuts.append(ts)
+    assert cuts == scene.cut_timestamps(sel) == [1.23333, 1.26667, 4.0, 13.3]
+
+
+def test_score_sequence_random_vs_numpy():
+    rng = np.random.default_rng(2)
+    sad = rng.integers(0, 255 * W * H, 200, dtype=np.uint64)
+    score, sel = oracle.scene_scores(sad, W, H, 0.3)
+    prev = 0.0
+    for t in range(1, 200):
+        mafd = float(sad[t]) / (W * H) / 1
+        diff = abs(mafd - prev)
+        want = float(np.clip(np.float32(min(mafd, diff) / 100.0), np.float32(0), np.float32(1)))
+        assert score[t] == want and sel[t] == (want > 0.3)
+        prev = mafd
+    assert score[0] == 0.0

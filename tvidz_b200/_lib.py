@@ -1,0 +1,64 @@
+"""ctypes binding of include/tvidz_b200.h.  There is no CPU fallback: if the CUDA
+library is missing or fails to load, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtvidz_b200.so")
+
+# every symbol include/tvidz_b200.h declares: (name, restype, argtypes)
+_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+SYMBOLS = [
+    ("tvz_last_error", C.c_char_p, []),
+    ("tvz_abi_version", _i, []),
+    ("tvz_sad_luma_u8", _i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _vp]),
+    ("tvz_sad_luma_u8_path", _i, [_vp, _i, _i, _i64, _i64, _i64]),
+    ("tvz_scene_select", _i, [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp]),
+    ("tvz_scene_score_host", _i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i, _d, _i, _vp, _vp, _vp]),
+    ("tvz_catalog_create", _i, [_vp, _vp, _vp, _i64, C.POINTER(_vp)]),
+    ("tvz_catalog_destroy", None, [_vp]),
+    ("tvz_catalog_rows", _i64, [_vp]),
+    ("tvz_catalog_values", _i64, [_vp]),
+    ("tvz_catalog_algo_bytes", _i64, [_vp]),
+    ("tvz_match_ws_create", _i, [_vp, _i64, C.POINTER(_vp)]),
+    ("tvz_match_ws_destroy", None, [_vp]),
+    ("tvz_catalog_match", _i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
+    ("tvz_catalog_match_async", _i, [_vp, _vp, _vp, _i, _i, _vp]),
+    ("tvz_match_ws_hits", _vp, [_vp]),
+    ("tvz_match_ws_nhits", _vp, [_vp]),
+    ("tvz_match_ws_counts", _vp, [_vp]),
+]
+# debug hooks outside the public header
+_DEBUG_SYMBOLS = [("tvz_debug_sad_tuning", _i, [_i, _i, _i, _i])]
+
+TVZ_ERR_OVERFLOW = -4
+_lib = None
+
+
+class TvzError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"tvidz_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; raise loudly (no fallback) when it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m tvidz_b200.build` "
+                "(nvcc, sm_100a). tvidz_b200 has no CPU path.")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS + _DEBUG_SYMBOLS:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise TvzError(rc, (lib().tvz_last_error() or b"").decode(errors="replace"))

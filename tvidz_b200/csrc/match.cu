@@ -1,0 +1,560 @@
+// Stage 2: find_duplicates over a device-resident packed catalogue.
+//
+// Replaces inspector/db.py:76-94 (full-table fetch at db.py:83 + the O(N*q*L) Python
+// membership loop at db.py:85-91).  Semantics:
+//     match_count(row) = #{ i : q[i] == some element of row }      (float ==)
+//     result = [(video_id, match_count) for rows with match_count >= min_match]
+//
+// Data layout in HBM (one shard per GPU):
+//     ts   : uint64 [n_vals]  IEEE-754 bit patterns of the stored timestamps, canonicalised
+//            at pack time (-0.0 -> +0.0, NaN dropped, in-row repeats dropped) so that bitwise
+//            equality == Python float equality and every stored value can add at most once
+//     off  : int64 [n_rows+1] CSR row offsets into ts
+//     vid  : int32 [n_rows]   videos.id of each row
+// Because in-row repeats are gone, match_count(row) = sum over stored values v of
+// mult(v), where mult(v) = number of query positions equal to v.  The count kernel is
+// therefore a pure streaming pass over `ts` (the only large array): 128-bit coalesced
+// loads, a shared-memory Bloom bitmap of the query rejects ~all values with one LDS, and
+// the rare survivors are looked up exactly and added to counts[row] with a RED.
+#include <algorithm>
+#include <unordered_set>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tvz {
+namespace {
+
+constexpr int kBloomBits = 1 << 16;          // 8 KB of shared memory
+constexpr int kBloomWords = kBloomBits / 32;
+constexpr int kMaxKeys = 2048;               // distinct query values per launch (24 KB smem)
+constexpr int kCountThreads = 512;
+constexpr int kCountUnroll = 4;              // 4 x 16 B in flight per thread
+constexpr int kScanThreads = 256;
+constexpr int kScanRowsPerThread = 8;
+constexpr int kScanRowsPerBlock = kScanThreads * kScanRowsPerThread;
+constexpr unsigned long long kPadPattern = 0x7ff8dead0000beefull;  // a NaN: never equals a stored value
+
+__host__ __device__ __forceinline__ uint32_t bloom_hash(unsigned long long v) {
+    uint32_t lo = static_cast<uint32_t>(v), hi = static_cast<uint32_t>(v >> 32);
+    uint32_t h = lo * 0x9E3779B1u ^ hi * 0x85EBCA77u;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    return h >> 16;  // kBloomBits = 2^16
+}
+
+// counts[row] += mult(v) for every stored value v that equals a query value.
+__global__ void __launch_bounds__(kCountThreads)
+match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs, const unsigned long long *__restrict__ keys,
+                   const int *__restrict__ mult, int n_keys, const long long *__restrict__ off, long long n_rows,
+                   int *__restrict__ counts) {
+    __shared__ uint32_t bloom[kBloomWords];
+    __shared__ unsigned long long skeys[kMaxKeys];
+    __shared__ int smult[kMaxKeys];
+    for (int i = threadIdx.x; i < kBloomWords; i += kCountThreads) bloom[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_keys; i += kCountThreads) {
+        const unsigned long long k = keys[i];
+        skeys[i] = k;
+        smult[i] = mult[i];
+        const uint32_t h = bloom_hash(k);
+        atomicOr(&bloom[h >> 5], 1u << (h & 31));
+    }
+    __syncthreads();
+
+    // exact path for the rare Bloom survivors
+    auto hit = [&](unsigned long long v, long long elem) {
+        int lo = 0, hi = n_keys;  // keys sorted ascending as uint64
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (skeys[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= n_keys || skeys[lo] != v) return;
+        long long a = 0, b = n_rows;  // last row with off[row] <= elem
+        while (b - a > 1) {
+            const long long mid = (a + b) >> 1;
+            if (off[mid] <= elem) a = mid; else b = mid;
+        }
+        atomicAdd(&counts[a], smult[lo]);
+    };
+    auto probe = [&](unsigned long long v, long long elem) {
+        const uint32_t h = bloom_hash(v);
+        if ((bloom[h >> 5] >> (h & 31)) & 1u) hit(v, elem);
+    };
+
+    const long long chunk = static_cast<long long>(kCountThreads) * kCountUnroll;
+    for (long long base = blockIdx.x * chunk; base < n_pairs; base += gridDim.x * chunk) {
+        ulonglong2 v[kCountUnroll];
+#pragma unroll
+        for (int j = 0; j < kCountUnroll; ++j) {
+            const long long i = base + j * kCountThreads + threadIdx.x;
+            v[j] = i < n_pairs ? __ldcs(ts2 + i) : make_ulonglong2(kPadPattern, kPadPattern);
+        }
+#pragma unroll
+        for (int j = 0; j < kCountUnroll; ++j) {
+            const long long i = base + j * kCountThreads + threadIdx.x;
+            probe(v[j].x, 2 * i);
+            probe(v[j].y, 2 * i + 1);
+        }
+    }
+}
+
+// Ordered compaction, pass 1: qualifying rows per block of kScanRowsPerBlock rows.
+__global__ void __launch_bounds__(kScanThreads)
+match_scan_kernel(const int *__restrict__ counts, long long n_rows, int min_match, int *__restrict__ block_hits) {
+    const long long r0 = blockIdx.x * static_cast<long long>(kScanRowsPerBlock) + threadIdx.x * kScanRowsPerThread;
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kScanRowsPerThread; ++j)
+        if (r0 + j < n_rows && counts[r0 + j] >= min_match) ++c;
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int ws[kScanThreads / 32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < kScanThreads / 32; ++i) t += ws[i];
+        block_hits[blockIdx.x] = t;
+    }
+}
+
+// Pass 2: each block sums the block_hits before it, then writes its qualifying rows in row
+// order and zeroes counts[] for the next query.  out: int32 [cap+1][2]; out[0] = {n_hits
+// (saturated), overflow flag}; out[1+h] = {video_id, match_count}.  rows_out[h] = row index.
+__global__ void __launch_bounds__(kScanThreads)
+match_emit_kernel(int *__restrict__ counts, long long n_rows, int min_match, const int *__restrict__ block_hits,
+                  int n_blocks, const int *__restrict__ vid, int *__restrict__ out, long long *__restrict__ rows_out,
+                  long long cap, long long *__restrict__ n_hits_out) {
+    __shared__ long long s_base;
+    __shared__ int ws[kScanThreads / 32];
+    // exclusive prefix over earlier blocks (+ grand total for the header, block 0 only)
+    long long before = 0, total = 0;
+    for (int i = threadIdx.x; i < n_blocks; i += kScanThreads) {
+        const int h = block_hits[i];
+        if (i < static_cast<int>(blockIdx.x)) before += h;
+        total += h;
+    }
+    // block-wide sums of two 64-bit values
+    auto block_sum = [&](long long v) {
+        unsigned lo = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(v & 0xffff));
+        unsigned hi = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(v >> 16));  // per-thread v < 2^47
+        long long w = (static_cast<long long>(hi) << 16) + lo;
+        __shared__ long long acc[kScanThreads / 32];
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) acc[threadIdx.x >> 5] = w;
+        __syncthreads();
+        long long t = 0;
+        for (int i = 0; i < kScanThreads / 32; ++i) t += acc[i];
+        return t;
+    };
+    before = block_sum(before);
+    if (blockIdx.x == 0) {
+        total = block_sum(total);
+        if (threadIdx.x == 0) {
+            *n_hits_out = total;
+            out[0] = total > 0x7fffffffll ? 0x7fffffff : static_cast<int>(total);
+            out[1] = total > cap ? 1 : 0;
+        }
+    }
+    const long long r0 = blockIdx.x * static_cast<long long>(kScanRowsPerBlock) + threadIdx.x * kScanRowsPerThread;
+    int cnt[kScanRowsPerThread];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < kScanRowsPerThread; ++j) {
+        cnt[j] = -1;
+        if (r0 + j < n_rows) {
+            const int c = counts[r0 + j];
+            if (c != 0) counts[r0 + j] = 0;
+            if (c >= min_match) { cnt[j] = c; ++mine; }
+        }
+    }
+    // exclusive scan of `mine` across the block (rows are thread-contiguous, so thread order = row order)
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((threadIdx.x & 31) >= d) incl += n;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < kScanThreads / 32; ++i) { const int t = ws[i]; ws[i] = run; run += t; }
+        s_base = before;
+    }
+    __syncthreads();
+    long long pos = s_base + ws[threadIdx.x >> 5] + (incl - mine);
+#pragma unroll
+    for (int j = 0; j < kScanRowsPerThread; ++j) {
+        if (cnt[j] >= 0) {
+            if (pos < cap) {
+                out[2 + 2 * pos] = vid[r0 + j];
+                out[3 + 2 * pos] = cnt[j];
+                rows_out[pos] = r0 + j;
+            }
+            ++pos;
+        }
+    }
+}
+
+// Per hit row: the 1-based query index at which the row reaches min_match.
+// One warp per hit; q_canon holds the canonicalised query in query order (NaNs left as NaN
+// bit patterns, which equal no stored value).
+__global__ void match_kth_kernel(const unsigned long long *__restrict__ ts, const long long *__restrict__ off,
+                                 const long long *__restrict__ rows, const int *__restrict__ out_hdr, long long cap,
+                                 const unsigned long long *__restrict__ q_canon, int qn, int min_match,
+                                 int *__restrict__ kth) {
+    const long long n_hits = min(static_cast<long long>(out_hdr[0]), cap);
+    const int lane = threadIdx.x & 31;
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long h = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; h < n_hits; h += warps) {
+        const long long r = rows[h];
+        const long long b = off[r], e = off[r + 1];
+        int c = 0, k = 0;
+        if (min_match >= 1) {
+            for (int i = 0; i < qn && k == 0; ++i) {
+                const unsigned long long v = q_canon[i];
+                bool found = false;
+                for (long long j = b + lane; j < e + ((32 - ((e - b) & 31)) & 31); j += 32) {
+                    const bool m = j < e && ts[j] == v;
+                    if (__any_sync(0xffffffffu, m)) { found = true; break; }
+                }
+                if (found && ++c >= min_match) k = i + 1;
+            }
+        }
+        if (lane == 0) kth[h] = k;
+    }
+}
+
+}  // namespace
+}  // namespace tvz
+
+using namespace tvz;
+
+struct tvz_catalog {
+    int device = 0;
+    long long n_rows = 0, n_vals = 0, n_pairs = 0;
+    unsigned long long *d_ts = nullptr;
+    long long *d_off = nullptr;
+    int *d_vid = nullptr;
+};
+
+struct tvz_match_ws {
+    const tvz_catalog *cat = nullptr;
+    long long cap = 0;
+    int n_blocks = 0;
+    int *d_counts = nullptr;       // [n_rows], zero between queries
+    int *d_block_hits = nullptr;   // [n_blocks]
+    int *d_out = nullptr;          // [cap+1][2]
+    long long *d_rows = nullptr;   // [cap]
+    int *d_kth = nullptr;          // [cap]
+    long long *d_nhits = nullptr;  // [1]
+    // query staging: keys u64 [kMaxKeys] | q_canon u64 [q_cap] | mult i32 [kMaxKeys]
+    unsigned long long *d_keys = nullptr, *d_qcanon = nullptr;
+    int *d_mult = nullptr;
+    uint8_t *h_stage = nullptr;    // pinned
+    size_t stage_bytes = 0;
+    int q_cap = 0;
+    int *h_out = nullptr;          // pinned [cap+1][2]
+    int *h_kth = nullptr;          // pinned [cap]
+    cudaStream_t stream = nullptr; // private stream for the synchronous entry point
+    cudaEvent_t staged = nullptr;  // the pinned staging buffer has been consumed
+    bool stage_busy = false;
+};
+
+namespace {
+
+inline unsigned long long canon_bits(double v) {
+    unsigned long long b;
+    memcpy(&b, &v, 8);
+    if (b == 0x8000000000000000ull) b = 0;  // -0.0 == 0.0 in Python
+    return b;
+}
+inline bool is_nan_bits(unsigned long long b) {
+    return (b & 0x7ff0000000000000ull) == 0x7ff0000000000000ull && (b & 0x000fffffffffffffull) != 0;
+}
+
+int ensure_query_capacity(tvz_match_ws *ws, int qn) {
+    if (qn <= ws->q_cap) return TVZ_OK;
+    int cap = std::max(256, ws->q_cap);
+    while (cap < qn) cap *= 2;
+    if (ws->stage_busy) { TVZ_CUDA(cudaEventSynchronize(ws->staged)); ws->stage_busy = false; }
+    if (ws->d_qcanon) cudaFree(ws->d_qcanon);
+    if (ws->h_stage) cudaFreeHost(ws->h_stage);
+    ws->d_qcanon = nullptr;
+    ws->h_stage = nullptr;
+    ws->q_cap = 0;
+    TVZ_CUDA(cudaMalloc(&ws->d_qcanon, sizeof(unsigned long long) * cap));
+    // staging holds, per launch chunk, keys+mult, and once the canonical query
+    ws->stage_bytes = sizeof(unsigned long long) * cap * 2 + sizeof(int) * cap + 64;
+    TVZ_CUDA(cudaHostAlloc(&ws->h_stage, ws->stage_bytes, cudaHostAllocDefault));
+    ws->q_cap = cap;
+    return TVZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_video_id, int64_t n_rows,
+                       tvz_catalog **out) {
+    TVZ_REQUIRE(out, "null out pointer");
+    *out = nullptr;
+    TVZ_REQUIRE(n_rows >= 0, "negative n_rows");
+    TVZ_REQUIRE(n_rows == 0 || (h_off && h_video_id), "null offsets/video ids");
+    TVZ_REQUIRE(n_rows == 0 || h_off[0] == 0, "offsets must start at 0");
+    for (int64_t r = 0; r < n_rows; ++r)
+        TVZ_REQUIRE(h_off[r + 1] >= h_off[r], "offsets must be non-decreasing (row %lld)", (long long)r);
+    const int64_t n_in = n_rows ? h_off[n_rows] : 0;
+    TVZ_REQUIRE(n_in == 0 || h_ts, "null timestamps");
+
+    // canonicalise: drop NaN, fold -0.0, drop in-row repeats (first occurrence kept)
+    std::vector<unsigned long long> ts;
+    ts.reserve(static_cast<size_t>(n_in) + 2);
+    std::vector<long long> off(static_cast<size_t>(n_rows) + 1, 0);
+    std::unordered_set<unsigned long long> seen;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const size_t start = ts.size();
+        bool ascending = true;
+        double last = 0;
+        for (int64_t j = h_off[r]; j < h_off[r + 1]; ++j) {
+            const double v = h_ts[j];
+            const unsigned long long b = canon_bits(v);
+            if (is_nan_bits(b)) continue;
+            if (ts.size() > start && !(v > last)) ascending = false;
+            last = v;
+            ts.push_back(b);
+        }
+        if (!ascending) {  // rare: unsorted or repeated values -> stable de-duplication
+            seen.clear();
+            size_t w = start;
+            for (size_t j = start; j < ts.size(); ++j)
+                if (seen.insert(ts[j]).second) ts[w++] = ts[j];
+            ts.resize(w);
+        }
+        off[r + 1] = static_cast<long long>(ts.size());
+    }
+    tvz_catalog *c = new tvz_catalog();
+    c->n_rows = n_rows;
+    c->n_vals = static_cast<long long>(ts.size());
+    c->n_pairs = (c->n_vals + 1) / 2;
+    while (static_cast<long long>(ts.size()) < 2 * c->n_pairs + 2) ts.push_back(kPadPattern);
+    cudaGetDevice(&c->device);
+    auto fail = [&](cudaError_t e, const char *what) {
+        set_error(TVZ_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        tvz_catalog_destroy(c);
+        return TVZ_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&c->d_ts, ts.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(ts)");
+    if ((e = cudaMalloc(&c->d_off, off.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(off)");
+    if ((e = cudaMalloc(&c->d_vid, std::max<size_t>(1, n_rows) * 4)) != cudaSuccess) return fail(e, "cudaMalloc(vid)");
+    if ((e = cudaMemcpy(c->d_ts, ts.data(), ts.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(ts)");
+    if ((e = cudaMemcpy(c->d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(off)");
+    if (n_rows && (e = cudaMemcpy(c->d_vid, h_video_id, n_rows * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(vid)");
+    *out = c;
+    return TVZ_OK;
+}
+
+void tvz_catalog_destroy(tvz_catalog *c) {
+    if (!c) return;
+    if (c->d_ts) cudaFree(c->d_ts);
+    if (c->d_off) cudaFree(c->d_off);
+    if (c->d_vid) cudaFree(c->d_vid);
+    delete c;
+}
+
+int64_t tvz_catalog_rows(const tvz_catalog *c) { return c ? c->n_rows : 0; }
+int64_t tvz_catalog_values(const tvz_catalog *c) { return c ? c->n_vals : 0; }
+int64_t tvz_catalog_algo_bytes(const tvz_catalog *c) { return c ? 8 * c->n_vals + 8 * (c->n_rows + 1) : 0; }
+
+int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_ws **out) {
+    TVZ_REQUIRE(cat && out, "null pointer");
+    *out = nullptr;
+    TVZ_REQUIRE(hit_capacity >= 0, "negative capacity");
+    tvz_match_ws *ws = new tvz_match_ws();
+    ws->cat = cat;
+    ws->cap = std::max<long long>(1, hit_capacity);
+    ws->n_blocks = static_cast<int>((cat->n_rows + kScanRowsPerBlock - 1) / kScanRowsPerBlock);
+    auto bail = [&](cudaError_t e, const char *what) {
+        set_error(TVZ_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        tvz_match_ws_destroy(ws);
+        return TVZ_ERR_CUDA;
+    };
+    cudaError_t e;
+    const size_t nr = std::max<long long>(1, cat->n_rows);
+    if ((e = cudaMalloc(&ws->d_counts, nr * 4)) != cudaSuccess) return bail(e, "cudaMalloc(counts)");
+    if ((e = cudaMemset(ws->d_counts, 0, nr * 4)) != cudaSuccess) return bail(e, "cudaMemset(counts)");
+    if ((e = cudaMalloc(&ws->d_block_hits, std::max(1, ws->n_blocks) * 4)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ws->d_out, (ws->cap + 1) * 8)) != cudaSuccess) return bail(e, "cudaMalloc(out)");
+    if ((e = cudaMemset(ws->d_out, 0, 8)) != cudaSuccess) return bail(e, "cudaMemset(out)");
+    if ((e = cudaMalloc(&ws->d_rows, ws->cap * 8)) != cudaSuccess) return bail(e, "cudaMalloc(rows)");
+    if ((e = cudaMalloc(&ws->d_kth, ws->cap * 4)) != cudaSuccess) return bail(e, "cudaMalloc(kth)");
+    if ((e = cudaMalloc(&ws->d_nhits, 8)) != cudaSuccess) return bail(e, "cudaMalloc(nhits)");
+    if ((e = cudaMemset(ws->d_nhits, 0, 8)) != cudaSuccess) return bail(e, "cudaMemset(nhits)");
+    if ((e = cudaMalloc(&ws->d_keys, kMaxKeys * 8)) != cudaSuccess) return bail(e, "cudaMalloc(keys)");
+    if ((e = cudaMalloc(&ws->d_mult, kMaxKeys * 4)) != cudaSuccess) return bail(e, "cudaMalloc(mult)");
+    if ((e = cudaHostAlloc(&ws->h_out, (ws->cap + 1) * 8, cudaHostAllocDefault)) != cudaSuccess)
+        return bail(e, "cudaHostAlloc(out)");
+    if ((e = cudaHostAlloc(&ws->h_kth, ws->cap * 4, cudaHostAllocDefault)) != cudaSuccess)
+        return bail(e, "cudaHostAlloc(kth)");
+    if ((e = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreateWithFlags(&ws->staged, cudaEventDisableTiming)) != cudaSuccess)
+        return bail(e, "cudaEventCreate");
+    int rc = ensure_query_capacity(ws, 256);
+    if (rc) { tvz_match_ws_destroy(ws); return rc; }
+    // the memsets above ran on the legacy stream; queries run on non-blocking streams
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail(e, "cudaDeviceSynchronize");
+    *out = ws;
+    return TVZ_OK;
+}
+
+void tvz_match_ws_destroy(tvz_match_ws *ws) {
+    if (!ws) return;
+    if (ws->stream) cudaStreamSynchronize(ws->stream);
+    if (ws->d_counts) cudaFree(ws->d_counts);
+    if (ws->d_block_hits) cudaFree(ws->d_block_hits);
+    if (ws->d_out) cudaFree(ws->d_out);
+    if (ws->d_rows) cudaFree(ws->d_rows);
+    if (ws->d_kth) cudaFree(ws->d_kth);
+    if (ws->d_nhits) cudaFree(ws->d_nhits);
+    if (ws->d_keys) cudaFree(ws->d_keys);
+    if (ws->d_mult) cudaFree(ws->d_mult);
+    if (ws->d_qcanon) cudaFree(ws->d_qcanon);
+    if (ws->h_stage) cudaFreeHost(ws->h_stage);
+    if (ws->h_out) cudaFreeHost(ws->h_out);
+    if (ws->h_kth) cudaFreeHost(ws->h_kth);
+    if (ws->staged) cudaEventDestroy(ws->staged);
+    if (ws->stream) cudaStreamDestroy(ws->stream);
+    delete ws;
+}
+
+const int32_t *tvz_match_ws_hits(const tvz_match_ws *ws) { return ws ? ws->d_out : nullptr; }
+const int64_t *tvz_match_ws_nhits(const tvz_match_ws *ws) {
+    return ws ? reinterpret_cast<const int64_t *>(ws->d_nhits) : nullptr;
+}
+const int32_t *tvz_match_ws_counts(const tvz_match_ws *ws) { return ws ? ws->d_counts : nullptr; }
+
+}  // extern "C"
+
+namespace {
+
+// Enqueue query upload + count + ordered compaction (+ kth) on `st`.  `want_kth` needs qn <= q_cap.
+int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match, bool want_kth,
+                  cudaStream_t st) {
+    TVZ_REQUIRE(cat && ws && ws->cat == cat, "workspace does not belong to this catalogue");
+    TVZ_REQUIRE(qn >= 0 && (qn == 0 || h_q), "bad query");
+    int rc = ensure_query_capacity(ws, std::max(qn, 1));
+    if (rc) return rc;
+    if (ws->stage_busy) { TVZ_CUDA(cudaEventSynchronize(ws->staged)); ws->stage_busy = false; }
+
+    // canonical query (query order) + sorted distinct keys with multiplicities
+    unsigned long long *h_qc = reinterpret_cast<unsigned long long *>(ws->h_stage);
+    unsigned long long *h_keys = h_qc + ws->q_cap;
+    int *h_mult = reinterpret_cast<int *>(h_keys + ws->q_cap);
+    std::vector<unsigned long long> sorted;
+    sorted.reserve(qn);
+    for (int i = 0; i < qn; ++i) {
+        const unsigned long long b = canon_bits(h_q[i]);
+        h_qc[i] = b;
+        if (!is_nan_bits(b)) sorted.push_back(b);
+    }
+    std::sort(sorted.begin(), sorted.end());
+    int nk = 0;
+    for (size_t i = 0; i < sorted.size();) {
+        size_t j = i;
+        while (j < sorted.size() && sorted[j] == sorted[i]) ++j;
+        h_keys[nk] = sorted[i];
+        h_mult[nk] = static_cast<int>(j - i);
+        ++nk;
+        i = j;
+    }
+    if (want_kth && qn > 0)
+        TVZ_CUDA(cudaMemcpyAsync(ws->d_qcanon, h_qc, sizeof(unsigned long long) * qn, cudaMemcpyHostToDevice, st));
+    if (cat->n_rows > 0) {
+        const int sms = num_sms();
+        const long long chunk = static_cast<long long>(kCountThreads) * kCountUnroll;
+        const long long want = (cat->n_pairs + chunk - 1) / chunk;
+        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, 4ll * sms)));
+        for (int k0 = 0; k0 < nk; k0 += kMaxKeys) {
+            const int n = std::min(kMaxKeys, nk - k0);
+            TVZ_CUDA(cudaMemcpyAsync(ws->d_keys, h_keys + k0, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, st));
+            TVZ_CUDA(cudaMemcpyAsync(ws->d_mult, h_mult + k0, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+            match_count_kernel<<<grid, kCountThreads, 0, st>>>(reinterpret_cast<const ulonglong2 *>(cat->d_ts),
+                                                               cat->n_pairs, ws->d_keys, ws->d_mult, n, cat->d_off,
+                                                               cat->n_rows, ws->d_counts);
+            TVZ_CUDA(cudaGetLastError());
+        }
+        match_scan_kernel<<<ws->n_blocks, kScanThreads, 0, st>>>(ws->d_counts, cat->n_rows, min_match,
+                                                                 ws->d_block_hits);
+        TVZ_CUDA(cudaGetLastError());
+        match_emit_kernel<<<ws->n_blocks, kScanThreads, 0, st>>>(ws->d_counts, cat->n_rows, min_match,
+                                                                 ws->d_block_hits, ws->n_blocks, cat->d_vid, ws->d_out,
+                                                                 ws->d_rows, ws->cap, ws->d_nhits);
+        TVZ_CUDA(cudaGetLastError());
+        if (want_kth) {
+            match_kth_kernel<<<2 * sms, 256, 0, st>>>(cat->d_ts, cat->d_off, ws->d_rows, ws->d_out, ws->cap,
+                                                      ws->d_qcanon, qn, min_match, ws->d_kth);
+            TVZ_CUDA(cudaGetLastError());
+        }
+    } else {
+        TVZ_CUDA(cudaMemsetAsync(ws->d_out, 0, 8, st));
+        TVZ_CUDA(cudaMemsetAsync(ws->d_nhits, 0, 8, st));
+    }
+    TVZ_CUDA(cudaEventRecord(ws->staged, st));
+    ws->stage_busy = true;
+    return TVZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match,
+                            void *stream) {
+    return enqueue_match(cat, ws, h_q, qn, min_match, false, static_cast<cudaStream_t>(stream));
+}
+
+int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q, int qn, int min_match,
+                      int32_t *out_video_id, int32_t *out_count, int32_t *out_kth, int64_t cap, int64_t *n_out) {
+    TVZ_REQUIRE(n_out, "null n_out");
+    *n_out = 0;
+    TVZ_REQUIRE(cap >= 0 && (cap == 0 || (out_video_id && out_count)), "bad output buffers");
+    int rc = enqueue_match(cat, ws, q, qn, min_match, out_kth != nullptr, ws ? ws->stream : nullptr);
+    if (rc) return rc;
+    cudaStream_t st = ws->stream;
+    // header + an optimistic first slice of the hit list in one copy
+    const long long first = std::min<long long>(ws->cap, 2048);
+    TVZ_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, (first + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (out_kth) TVZ_CUDA(cudaMemcpyAsync(ws->h_kth, ws->d_kth, first * 4, cudaMemcpyDeviceToHost, st));
+    TVZ_CUDA(cudaStreamSynchronize(st));
+    ws->stage_busy = false;
+    long long n_hits = ws->h_out[0];
+    if (n_hits == 0x7fffffff) {
+        TVZ_CUDA(cudaMemcpy(&n_hits, ws->d_nhits, 8, cudaMemcpyDeviceToHost));
+    }
+    *n_out = n_hits;
+    if (n_hits > ws->cap || n_hits > cap)
+        return set_error(TVZ_ERR_OVERFLOW, "%lld rows qualify; workspace capacity %lld, caller capacity %lld",
+                         n_hits, ws->cap, (long long)cap);
+    if (n_hits > first) {
+        TVZ_CUDA(cudaMemcpyAsync(ws->h_out + 2 * (first + 1), ws->d_out + 2 * (first + 1), (n_hits - first) * 8,
+                                 cudaMemcpyDeviceToHost, st));
+        if (out_kth)
+            TVZ_CUDA(cudaMemcpyAsync(ws->h_kth + first, ws->d_kth + first, (n_hits - first) * 4,
+                                     cudaMemcpyDeviceToHost, st));
+        TVZ_CUDA(cudaStreamSynchronize(st));
+    }
+    for (long long h = 0; h < n_hits; ++h) {
+        out_video_id[h] = ws->h_out[2 + 2 * h];
+        out_count[h] = ws->h_out[3 + 2 * h];
+    }
+    if (out_kth) memcpy(out_kth, ws->h_kth, n_hits * 4);
+    return TVZ_OK;
+}
+
+}  // extern "C"
