@@ -115,13 +115,18 @@ int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q,
 
 /* Device-resident variant for pipelines, CUDA graphs and the sharded matcher:
  * enqueues the query upload, the count kernel and the ordered compaction on
- * `stream` and returns without synchronising.  Results stay on the device:
- *   tvz_match_ws_hits():  int32 [hit_capacity][2] = (video_id, match_count)
- *   tvz_match_ws_nhits(): int64, the number of qualifying rows (may exceed capacity;
- *                         only the first hit_capacity are stored)
+ * `stream` and returns without synchronising.  The result is written to
+ *   d_out : int32 [out_cap + 1][2] on the device (NULL = the workspace's own
+ *           buffer, see tvz_match_ws_hits, capacity = hit_capacity):
+ *             d_out[0]     = { n_hits saturated to INT32_MAX, 1 if n_hits > out_cap }
+ *             d_out[1 + h] = { video_id, match_count } of the h-th qualifying row
+ *           -- one fixed-size record a collective can gather as is.
+ *   tvz_match_ws_nhits(): int64, the exact number of qualifying rows.
+ * out_cap must not exceed the workspace's hit_capacity.  h_q is consumed before
+ * the call returns (it is staged into pinned memory owned by the workspace).
  */
 int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn,
-                            int min_match, void *stream);
+                            int min_match, int32_t *d_out, int64_t out_cap, void *stream);
 const int32_t *tvz_match_ws_hits(const tvz_match_ws *ws);
 const int64_t *tvz_match_ws_nhits(const tvz_match_ws *ws);
 const int32_t *tvz_match_ws_counts(const tvz_match_ws *ws);  /* int32 [rows] scratch (zero between calls) */

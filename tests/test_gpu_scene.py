@@ -1,0 +1,154 @@
+"""Stage 1 parity on the GPU: the CUDA path (through the C ABI) against the CPU oracle on
+the same seeded inputs -- bit-exact integer SADs, scores, selections and cut lists."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import tvidz_b200._lib as L
+from tvidz_b200 import scene, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(frames_cpu: torch.Tensor, dev, width=None, threshold=0.3, expect_path=None):
+    f = frames_cpu.numpy()
+    S, F, H, P = f.shape
+    W = P if width is None else width
+    o_sad, o_score, o_sel, _ = oracle.scene_batch(np.ascontiguousarray(f), W, threshold)
+    d = frames_cpu.to(dev)
+    if expect_path is not None:
+        pitch, fs, ss = scene._strides(d)
+        assert L.lib().tvz_sad_luma_u8_path(d.data_ptr(), W, H, pitch, fs, ss) == expect_path
+    sad, score, sel = scene.score_frames(d, W, threshold)
+    torch.cuda.synchronize()
+    assert np.array_equal(sad.cpu().numpy().astype(np.uint64), o_sad)
+    assert np.array_equal(score.cpu().numpy(), o_score)           # bit-exact doubles
+    assert np.array_equal(sel.cpu().numpy(), o_sel)
+    return o_sad, o_sel
+
+
+@pytest.mark.parametrize("S,F,H,W", [(1, 2, 16, 16), (3, 9, 48, 64), (2, 33, 270, 480), (5, 7, 1, 4096),
+                                     (1, 5, 1080, 1920), (4, 18, 720, 1280), (2, 3, 2160, 3840)])
+def test_flat_layout_random(cuda, S, F, H, W):
+    g = torch.Generator().manual_seed(S * 1000 + F)
+    frames = torch.randint(0, 256, (S, F, H, W), dtype=torch.uint8, generator=g)
+    _check(frames, cuda, expect_path=1)
+
+
+@pytest.mark.parametrize("S,F,H,W,P", [(2, 6, 33, 64, 128), (1, 4, 1080, 1920, 2048), (3, 5, 17, 4096, 4112),
+                                       (2, 9, 2160, 3840, 4096)])
+def test_row_band_layout_pitch_gt_width(cuda, S, F, H, W, P):
+    g = torch.Generator().manual_seed(P)
+    frames = torch.randint(0, 256, (S, F, H, P), dtype=torch.uint8, generator=g)   # random padding too
+    _check(frames, cuda, width=W, expect_path=1)
+
+
+@pytest.mark.parametrize("S,F,H,W,P", [(2, 5, 31, 1918, 1984), (1, 4, 9, 13, 13), (3, 3, 20, 50, 51),
+                                       (1, 6, 270, 479, 479), (2, 4, 5, 1, 7)])
+def test_generic_layouts(cuda, S, F, H, W, P):
+    g = torch.Generator().manual_seed(W)
+    frames = torch.randint(0, 256, (S, F, H, P), dtype=torch.uint8, generator=g)
+    _check(frames, cuda, width=W, expect_path=0)
+
+
+def test_unaligned_base_takes_generic_path(cuda):
+    g = torch.Generator().manual_seed(1)
+    big = torch.randint(0, 256, (2 * 6 * 32 * 64 + 16,), dtype=torch.uint8, generator=g)
+    view_cpu = big[3:3 + 2 * 6 * 32 * 64].view(2, 6, 32, 64)
+    d = big.to(cuda)[3:3 + 2 * 6 * 32 * 64].view(2, 6, 32, 64)
+    assert L.lib().tvz_sad_luma_u8_path(d.data_ptr(), 64, 32, 64, 32 * 64, 6 * 32 * 64) == 0
+    sad = scene.sad_luma(d)
+    o_sad, _, _, _ = oracle.scene_batch(np.ascontiguousarray(view_cpu.numpy()))
+    assert np.array_equal(sad.cpu().numpy().astype(np.uint64), o_sad)
+
+
+def test_known_answers_1080p(cuda):
+    """SURVEY.md A.5 #1-#4 at full 1920x1080 through the CUDA path."""
+    H, W = 1080, 1920
+    mk = lambda vals: torch.stack([torch.full((H, W), v, dtype=torch.uint8) for v in vals])[None]
+    sad, score, sel = scene.score_frames(mk([77, 77, 77]).to(cuda))
+    assert sad.tolist() == [[0, 0, 0]] and sel.tolist() == [[0, 0, 0]]
+    sad, score, sel = scene.score_frames(mk([0, 255, 255]).to(cuda))
+    assert sad.tolist() == [[0, 528768000, 0]] and score.tolist() == [[0.0, 1.0, 0.0]] and sel.tolist() == [[0, 1, 0]]
+    sad, score, sel = scene.score_frames(mk([0, 30]).to(cuda))
+    assert sad[0, 1].item() == 62208000 and score[0, 1].item() == float(np.float32(0.3)) and sel[0, 1].item() == 1
+    f = mk([0, 30])
+    f[0, 1, 0, 0] = 29                                      # sad = 62,207,999 -> float32 0.29999998 -> no cut
+    sad, score, sel = scene.score_frames(f.to(cuda))
+    assert sad[0, 1].item() == 62207999 and score[0, 1].item() < 0.3 and sel[0, 1].item() == 0
+    sad, score, sel = scene.score_frames(mk([0, 40, 80, 120, 160, 200]).to(cuda))
+    assert sel.tolist() == [[0, 1, 0, 0, 0, 0]] and score[0, 1].item() == float(np.float32(0.4))
+
+
+def test_max_sad_4k_fits(cuda):
+    H, W = 2160, 3840
+    f = torch.zeros((1, 3, H, W), dtype=torch.uint8)
+    f[0, 1] = 255
+    sad = scene.sad_luma(f.to(cuda))
+    assert sad.tolist() == [[0, 2115072000, 2115072000]]
+
+
+def test_empty_and_single_frame(cuda):
+    f = torch.zeros((2, 1, 8, 16), dtype=torch.uint8, device=cuda)
+    sad, score, sel = scene.score_frames(f)
+    assert sad.tolist() == [[0], [0]] and score.tolist() == [[0.0], [0.0]] and sel.tolist() == [[0], [0]]
+    assert scene.sad_luma(torch.zeros((0, 4, 8, 16), dtype=torch.uint8, device=cuda)).shape == (0, 4)
+
+
+@pytest.mark.parametrize("variant,ctas,units,minseg", [(0, 0, 16, 16), (1, 0, 1, 1), (2, 2, 64, 2), (3, 1, 4, 4),
+                                                       (4, 0, 16, 3), (5, 1, 200, 1)])
+def test_ring_variants_and_time_segments(cuda, variant, ctas, units, minseg):
+    """Every ring geometry and aggressive time segmentation give the same integers."""
+    frames = synth.synth_frames(3, 41, 90, 160, seed=variant, scene_len=(4, 11))
+    try:
+        L.check(L.lib().tvz_debug_sad_tuning(variant, ctas, units, minseg))
+        _, o_sel = _check(frames, cuda, expect_path=1)
+        assert o_sel.sum() >= 6                                  # the synthetic cuts are really there
+    finally:
+        L.check(L.lib().tvz_debug_sad_tuning(0, 0, 16, 16))
+
+
+def test_synthetic_streams_cut_lists(cuda):
+    """Synthetic scenes: exactly one cut per scene change, cut lists identical
+    to the oracle's, device-resident and host-buffer entries alike."""
+    frames = synth.synth_frames(4, 64, 135, 240, seed=7, scene_len=(5, 20))
+    f = frames.numpy()
+    _, _, o_sel, _ = oracle.scene_batch(f)
+    want = [oracle.cut_timestamps(o_sel[s]) for s in range(4)]
+    assert all(len(w) >= 2 for w in want)
+    assert scene.detect_scene_cuts(frames.to(cuda)) == want
+    assert scene.detect_scene_cuts(frames.pin_memory()) == want          # host-buffer entry (torch)
+    assert scene.detect_scene_cuts(f) == want                            # host-buffer entry (numpy)
+    assert scene.detect_scene_cuts(frames[0].to(cuda)) == want[0]
+
+
+@pytest.mark.parametrize("chunk", [1, 2, 5, 7, 64, 0])
+def test_host_entry_chunking(cuda, chunk):
+    frames = synth.synth_frames(3, 23, 54, 96, seed=chunk, scene_len=(3, 9)).pin_memory()
+    o_sad, o_score, o_sel, _ = oracle.scene_batch(frames.numpy())
+    sad, score, sel = scene.score_frames_host(frames, chunk_frames=chunk)
+    assert np.array_equal(sad, o_sad) and np.array_equal(score, o_score) and np.array_equal(sel, o_sel)
+
+
+def test_host_entry_padded_rows(cuda):
+    frames = synth.synth_frames(2, 12, 30, 50, seed=3, scene_len=(3, 6), pitch=64)
+    o_sad, o_score, o_sel, _ = oracle.scene_batch(frames.numpy(), 50)
+    sad, score, sel = scene.score_frames_host(frames.numpy(), width=50, chunk_frames=5)
+    assert np.array_equal(sad, o_sad) and np.array_equal(sel, o_sel)
+
+
+def test_full_size_properties(cuda):
+    """BASELINE config 2 geometry (64 streams of 1080p; fewer frames): size-independent checks
+    -- time reversal leaves each SAD in place mirrored, a constant offset on both frames
+    changes nothing, and a sampled stream equals the oracle."""
+    S, F, H, W = 64, 6, 1080, 1920
+    g = torch.Generator(device=cuda).manual_seed(5)
+    frames = torch.randint(16, 236, (S, F, H, W), dtype=torch.uint8, device=cuda, generator=g)
+    sad = scene.sad_luma(frames)
+    rev = scene.sad_luma(frames.flip(1).contiguous())
+    assert torch.equal(sad[:, 1:], rev[:, 1:].flip(1))
+    assert torch.equal(scene.sad_luma(frames + 7), sad)
+    for s in (0, 37, 63):
+        o_sad, _, _, _ = oracle.scene_batch(frames[s:s + 1].cpu().numpy())
+        assert np.array_equal(sad[s:s + 1].cpu().numpy().astype(np.uint64), o_sad)

@@ -109,6 +109,20 @@ class Catalogue:
             return t.vid[:n].copy(), t.cnt[:n].copy(), t.kth[:n].copy()
         return t.vid[:n].copy(), t.cnt[:n].copy()
 
+    def match_async(self, new_timestamps, min_match: int, out: torch.Tensor, stream=None) -> None:
+        """Enqueue one query on `stream` (default: torch's current stream) and return at once.
+        `out`: int32 CUDA tensor [cap + 1, 2] receiving the fixed-size record described in
+        include/tvidz_b200.h (row 0 = [n_hits, overflow], then (video_id, match_count))."""
+        if out.dtype != torch.int32 or out.dim() != 2 or out.shape[1] != 2 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous int32 [cap + 1, 2] tensor")
+        cap = out.shape[0] - 1
+        q = np.ascontiguousarray(np.asarray(new_timestamps, dtype=np.float64).reshape(-1))
+        ws = self._ws(cap)
+        st = torch.cuda.current_stream(self.device) if stream is None else stream
+        with torch.cuda.device(self.device):
+            check(lib().tvz_catalog_match_async(self._handle, ws, q.ctypes.data, q.shape[0], int(min_match),
+                                                out.data_ptr(), cap, int(st.cuda_stream)))
+
     def find_duplicates(self, new_timestamps, min_match: int = 5) -> list[tuple[int, int]]:
         """db.py:76-94: list of (video_id, match_count) tuples of Python ints."""
         vid, cnt = self.match(new_timestamps, min_match)

@@ -445,9 +445,11 @@ namespace {
 
 // Enqueue query upload + count + ordered compaction (+ kth) on `st`.  `want_kth` needs qn <= q_cap.
 int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match, bool want_kth,
-                  cudaStream_t st) {
+                  int *d_out, long long out_cap, cudaStream_t st) {
     TVZ_REQUIRE(cat && ws && ws->cat == cat, "workspace does not belong to this catalogue");
     TVZ_REQUIRE(qn >= 0 && (qn == 0 || h_q), "bad query");
+    if (!d_out) { d_out = ws->d_out; out_cap = ws->cap; }
+    TVZ_REQUIRE(out_cap >= 1 && out_cap <= ws->cap, "output capacity %lld outside [1, %lld]", out_cap, ws->cap);
     int rc = ensure_query_capacity(ws, std::max(qn, 1));
     if (rc) return rc;
     if (ws->stage_busy) { TVZ_CUDA(cudaEventSynchronize(ws->staged)); ws->stage_busy = false; }
@@ -493,16 +495,16 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
                                                                  ws->d_block_hits);
         TVZ_CUDA(cudaGetLastError());
         match_emit_kernel<<<ws->n_blocks, kScanThreads, 0, st>>>(ws->d_counts, cat->n_rows, min_match,
-                                                                 ws->d_block_hits, ws->n_blocks, cat->d_vid, ws->d_out,
-                                                                 ws->d_rows, ws->cap, ws->d_nhits);
+                                                                 ws->d_block_hits, ws->n_blocks, cat->d_vid, d_out,
+                                                                 ws->d_rows, out_cap, ws->d_nhits);
         TVZ_CUDA(cudaGetLastError());
         if (want_kth) {
-            match_kth_kernel<<<2 * sms, 256, 0, st>>>(cat->d_ts, cat->d_off, ws->d_rows, ws->d_out, ws->cap,
+            match_kth_kernel<<<2 * sms, 256, 0, st>>>(cat->d_ts, cat->d_off, ws->d_rows, d_out, out_cap,
                                                       ws->d_qcanon, qn, min_match, ws->d_kth);
             TVZ_CUDA(cudaGetLastError());
         }
     } else {
-        TVZ_CUDA(cudaMemsetAsync(ws->d_out, 0, 8, st));
+        TVZ_CUDA(cudaMemsetAsync(d_out, 0, 8, st));
         TVZ_CUDA(cudaMemsetAsync(ws->d_nhits, 0, 8, st));
     }
     TVZ_CUDA(cudaEventRecord(ws->staged, st));
@@ -515,8 +517,8 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
 extern "C" {
 
 int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match,
-                            void *stream) {
-    return enqueue_match(cat, ws, h_q, qn, min_match, false, static_cast<cudaStream_t>(stream));
+                            int32_t *d_out, int64_t out_cap, void *stream) {
+    return enqueue_match(cat, ws, h_q, qn, min_match, false, d_out, out_cap, static_cast<cudaStream_t>(stream));
 }
 
 int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q, int qn, int min_match,
@@ -524,7 +526,7 @@ int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q,
     TVZ_REQUIRE(n_out, "null n_out");
     *n_out = 0;
     TVZ_REQUIRE(cap >= 0 && (cap == 0 || (out_video_id && out_count)), "bad output buffers");
-    int rc = enqueue_match(cat, ws, q, qn, min_match, out_kth != nullptr, ws ? ws->stream : nullptr);
+    int rc = enqueue_match(cat, ws, q, qn, min_match, out_kth != nullptr, nullptr, 0, ws ? ws->stream : nullptr);
     if (rc) return rc;
     cudaStream_t st = ws->stream;
     // header + an optimistic first slice of the hit list in one copy

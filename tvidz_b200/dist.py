@@ -1,0 +1,100 @@
+"""Multi-GPU matcher: the catalogue is sharded by row across the ranks of one box, every
+rank streams its own shard, and the only data-path collective is one all-gather of the
+fixed-size per-shard hit records.  One process per GPU, torch.distributed
+for the plumbing (NCCL on GPUs; the host logic is backend-agnostic and is tested with gloo).
+
+Scene scoring does not shard -- streams are independent ("replicas only").
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(off: np.ndarray, world: int) -> list[tuple[int, int]]:
+    """Contiguous row ranges per rank, balanced by stored values (sum of row lengths), not by
+    row count.  Concatenating the shards in rank order restores catalogue order."""
+    off = np.asarray(off, np.int64)
+    n = off.shape[0] - 1
+    total = int(off[-1]) if n > 0 else 0
+    cuts = [0]
+    for r in range(1, world):
+        target = (total * r) // world
+        cuts.append(max(int(np.searchsorted(off, target, side="left")), cuts[-1]))
+    cuts.append(n)
+    cuts = [min(c, n) for c in cuts]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def take_shard(ts: np.ndarray, off: np.ndarray, video_id: np.ndarray, lo: int, hi: int):
+    off = np.asarray(off, np.int64)
+    return (np.ascontiguousarray(ts[off[lo]:off[hi]]), np.ascontiguousarray(off[lo:hi + 1] - off[lo]),
+            np.ascontiguousarray(video_id[lo:hi]))
+
+
+def merge_records(gathered: np.ndarray, cap: int):
+    """gathered: int32 [world, cap + 1, 2] of per-shard records -> (pairs int32 [n, 2] in
+    catalogue order, overflowed: bool, needed: int = largest per-shard hit count)."""
+    parts, overflow, needed = [], False, 0
+    for rec in gathered:
+        n, flag = int(rec[0, 0]), int(rec[0, 1])
+        needed = max(needed, n)
+        if flag or n > cap:
+            overflow = True
+            continue
+        parts.append(rec[1:1 + n])
+    pairs = np.concatenate(parts) if parts else np.zeros((0, 2), np.int32)
+    return pairs, overflow, needed
+
+
+class ShardedCatalogue:
+    """find_duplicates over a catalogue sharded across the ranks of the default process group.
+
+    `local_factory(ts, off, video_id)` builds the per-rank matcher; it must offer
+    ``match_async(q, min_match, out)`` filling an int32 [cap + 1, 2] record tensor on the
+    rank's device.  The default is the CUDA `Catalogue` (no CPU path in the product; the
+    gloo tests inject a CPU stand-in to exercise this host logic).
+    """
+
+    def __init__(self, ts, off, video_id, hit_capacity: int = 1 << 15, device=None,
+                 local_factory: Callable | None = None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.bounds = shard_bounds(off, self.world)
+        lo, hi = self.bounds[self.rank]
+        s_ts, s_off, s_vid = take_shard(np.asarray(ts), np.asarray(off), np.asarray(video_id), lo, hi)
+        if local_factory is None:
+            from .catalog import Catalogue
+            dev = torch.cuda.current_device() if device is None else device
+            self.device = torch.device("cuda", dev)
+            self.local = Catalogue(s_ts, s_off, s_vid, device=dev, hit_capacity=hit_capacity)
+        else:
+            self.device = torch.device("cpu") if device is None else torch.device(device)
+            self.local = local_factory(s_ts, s_off, s_vid)
+        self.n_rows_local = hi - lo
+        self.n_values_local = int(s_off[-1]) if s_off.size else 0
+        self._alloc(hit_capacity)
+
+    def _alloc(self, cap: int) -> None:
+        self.cap = int(cap)
+        self.record = torch.zeros((self.cap + 1, 2), dtype=torch.int32, device=self.device)
+        self.gathered = torch.zeros((self.world * (self.cap + 1), 2), dtype=torch.int32, device=self.device)
+
+    def enqueue(self, new_timestamps, min_match: int) -> None:
+        """Local count + compaction, then the all-gather, all on the current stream."""
+        self.local.match_async(new_timestamps, min_match, self.record)
+        dist.all_gather_into_tensor(self.gathered, self.record, group=self.group)
+
+    def find_duplicates(self, new_timestamps, min_match: int = 5) -> list[tuple[int, int]]:
+        """Every rank returns the full list [(video_id, match_count)] in catalogue order."""
+        while True:
+            self.enqueue(new_timestamps, min_match)
+            pairs, overflow, needed = merge_records(
+                self.gathered.view(self.world, self.cap + 1, 2).cpu().numpy(), self.cap)
+            if not overflow:
+                return [(int(v), int(c)) for v, c in pairs]
+            self._alloc(max(needed, 2 * self.cap))     # every rank sees the same records -> same decision
