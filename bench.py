@@ -101,7 +101,7 @@ def cpu_scoring_baseline(frames_np: np.ndarray, budget_s: float = 10.0):
     """The C restatement of FFmpeg's scene score on all host cores, one stream per thread."""
     import oracle
     S, F = frames_np.shape[:2]
-    oracle.scene_batch(frames_np[: min(S, 8), : min(F, 4)])            # warm (page-in, thread pool)
+    oracle.scene_batch(np.ascontiguousarray(frames_np[: min(S, 8), : min(F, 4)]))            # warm (page-in, thread pool)
     done, t0, used = 0, time.perf_counter(), 1
     while True:
         _, _, _, used = oracle.scene_batch(frames_np)

@@ -115,7 +115,7 @@ def test_unsorted_rows_repeats_and_specials(cuda):
 
 def test_query_longer_than_one_launch(cuda):
     """More distinct query values than one launch holds (2048): the count accumulates."""
-    ts, off, vid = synth.synth_catalogue(3000, len_range=(1, 50), gap_range=(1, 5), seed=6)
+    ts, off, vid = synth.synth_catalogue(3000, len_range=(1, 50), gap_range=(1, 300), seed=6)
     cat = Catalogue(ts, off, vid)
     q = np.unique(ts)[:5000]
     assert q.shape[0] > 4096

@@ -25,77 +25,102 @@
 namespace tvz {
 namespace {
 
-constexpr int kBloomBits = 1 << 16;          // 8 KB of shared memory
-constexpr int kBloomWords = kBloomBits / 32;
-constexpr int kMaxKeys = 2048;               // distinct query values per launch (24 KB smem)
+constexpr int kMapEntries = 1 << 16;         // byte-map filter of the query: 64 KB of shared memory
+constexpr int kMaxKeys = 2048;               // distinct query values per launch
 constexpr int kCountThreads = 512;
 constexpr int kCountUnroll = 4;              // 4 x 16 B in flight per thread
+constexpr int kChunkPairs = kCountThreads * kCountUnroll;  // 2048 pairs = 4096 values per CTA iteration
+constexpr int kQueueCap = 1024;              // filter survivors parked per iteration
+constexpr int kBlockShift = 10;              // coarse row index: one entry per 1024 stored values
 constexpr int kScanThreads = 256;
 constexpr int kScanRowsPerThread = 8;
 constexpr int kScanRowsPerBlock = kScanThreads * kScanRowsPerThread;
 constexpr unsigned long long kPadPattern = 0x7ff8dead0000beefull;  // a NaN: never equals a stored value
 
-__host__ __device__ __forceinline__ uint32_t bloom_hash(unsigned long long v) {
-    uint32_t lo = static_cast<uint32_t>(v), hi = static_cast<uint32_t>(v >> 32);
-    uint32_t h = lo * 0x9E3779B1u ^ hi * 0x85EBCA77u;
-    h ^= h >> 15;
-    h *= 0x2C1B3C6Du;
-    return h >> 16;  // kBloomBits = 2^16
+struct alignas(16) CountSmem {
+    unsigned char map[kMapEntries];   // first: zeroed with 16-byte stores
+    unsigned long long keys[kMaxKeys];
+    unsigned long long qv[kQueueCap];
+    int mult[kMaxKeys];
+    unsigned qo[kQueueCap];
+    unsigned qcount[2];
+};
+
+// Two IMADs and a shift: good enough on frame-quantised timestamps and on x.0 / x.5 values
+// (false-positive rate ~ n_keys / 65536, measured in DESIGN.md).
+__host__ __device__ __forceinline__ uint32_t filter_hash(unsigned long long v) {
+    const uint32_t lo = static_cast<uint32_t>(v), hi = static_cast<uint32_t>(v >> 32);
+    return (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> 16;
 }
 
 // counts[row] += mult(v) for every stored value v that equals a query value.
-__global__ void __launch_bounds__(kCountThreads)
-match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs, const unsigned long long *__restrict__ keys,
-                   const int *__restrict__ mult, int n_keys, const long long *__restrict__ off, long long n_rows,
+//
+// Streaming pass over `ts` (padded to whole chunks, so the hot loop has no bounds checks):
+// per value one hash, one LDS.U8 and a branch.  Survivors (true matches plus ~0.1% false
+// positives) are parked in a shared-memory queue and resolved after the chunk by all threads
+// together -- exact key lookup, then the row through a coarse index (row of every 1024th
+// value) and a short search in `off` -- so a hit never stalls the other 31 lanes of its warp.
+__global__ void __launch_bounds__(kCountThreads, 2)
+match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
+                   const unsigned long long *__restrict__ keys, const int *__restrict__ mult, int n_keys,
+                   const long long *__restrict__ off, const int *__restrict__ block_row, long long n_rows,
                    int *__restrict__ counts) {
-    __shared__ uint32_t bloom[kBloomWords];
-    __shared__ unsigned long long skeys[kMaxKeys];
-    __shared__ int smult[kMaxKeys];
-    for (int i = threadIdx.x; i < kBloomWords; i += kCountThreads) bloom[i] = 0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CountSmem &sm = *reinterpret_cast<CountSmem *>(smem_raw);
+    for (int i = threadIdx.x; i < kMapEntries / 16; i += kCountThreads)
+        reinterpret_cast<uint4 *>(sm.map)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < 2) sm.qcount[threadIdx.x] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < n_keys; i += kCountThreads) {
         const unsigned long long k = keys[i];
-        skeys[i] = k;
-        smult[i] = mult[i];
-        const uint32_t h = bloom_hash(k);
-        atomicOr(&bloom[h >> 5], 1u << (h & 31));
+        sm.keys[i] = k;
+        sm.mult[i] = mult[i];
+        sm.map[filter_hash(k)] = 1;
     }
     __syncthreads();
 
-    // exact path for the rare Bloom survivors
-    auto hit = [&](unsigned long long v, long long elem) {
+    auto resolve = [&](unsigned long long v, long long elem) {
         int lo = 0, hi = n_keys;  // keys sorted ascending as uint64
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (skeys[mid] < v) lo = mid + 1; else hi = mid;
+            if (sm.keys[mid] < v) lo = mid + 1; else hi = mid;
         }
-        if (lo >= n_keys || skeys[lo] != v) return;
-        long long a = 0, b = n_rows;  // last row with off[row] <= elem
-        while (b - a > 1) {
-            const long long mid = (a + b) >> 1;
-            if (off[mid] <= elem) a = mid; else b = mid;
+        if (lo >= n_keys || sm.keys[lo] != v) return;  // filter false positive
+        const long long b = elem >> kBlockShift;
+        long long a = block_row[b], z = block_row[b + 1] + 1;  // last row with off[row] <= elem is in [a, z)
+        while (z - a > 1) {
+            const long long mid = (a + z) >> 1;
+            if (off[mid] <= elem) a = mid; else z = mid;
         }
-        atomicAdd(&counts[a], smult[lo]);
-    };
-    auto probe = [&](unsigned long long v, long long elem) {
-        const uint32_t h = bloom_hash(v);
-        if ((bloom[h >> 5] >> (h & 31)) & 1u) hit(v, elem);
+        atomicAdd(&counts[a], sm.mult[lo]);
     };
 
-    const long long chunk = static_cast<long long>(kCountThreads) * kCountUnroll;
-    for (long long base = blockIdx.x * chunk; base < n_pairs; base += gridDim.x * chunk) {
+    unsigned it = 0;
+    for (long long base = static_cast<long long>(blockIdx.x) * kChunkPairs; base < n_pairs_padded;
+         base += static_cast<long long>(gridDim.x) * kChunkPairs, ++it) {
+        const ulonglong2 *src = ts2 + base + threadIdx.x;
         ulonglong2 v[kCountUnroll];
 #pragma unroll
-        for (int j = 0; j < kCountUnroll; ++j) {
-            const long long i = base + j * kCountThreads + threadIdx.x;
-            v[j] = i < n_pairs ? __ldcs(ts2 + i) : make_ulonglong2(kPadPattern, kPadPattern);
-        }
+        for (int j = 0; j < kCountUnroll; ++j) v[j] = __ldcs(src + j * kCountThreads);
+        unsigned *qc = &sm.qcount[it & 1];
+        auto probe = [&](unsigned long long x, unsigned rel) {
+            if (sm.map[filter_hash(x)]) {
+                const unsigned slot = atomicAdd(qc, 1u);
+                if (slot < kQueueCap) { sm.qv[slot] = x; sm.qo[slot] = rel; }
+                else resolve(x, 2 * base + rel);  // queue full (dense matches): resolve in place
+            }
+        };
 #pragma unroll
         for (int j = 0; j < kCountUnroll; ++j) {
-            const long long i = base + j * kCountThreads + threadIdx.x;
-            probe(v[j].x, 2 * i);
-            probe(v[j].y, 2 * i + 1);
+            const unsigned rel = 2u * (j * kCountThreads + threadIdx.x);
+            probe(v[j].x, rel);
+            probe(v[j].y, rel + 1u);
         }
+        __syncthreads();
+        const unsigned n = min(*qc, static_cast<unsigned>(kQueueCap));
+        if (threadIdx.x == 0) sm.qcount[(it + 1) & 1] = 0;
+        for (unsigned i = threadIdx.x; i < n; i += kCountThreads) resolve(sm.qv[i], 2 * base + sm.qo[i]);
+        __syncthreads();
     }
 }
 
@@ -234,9 +259,11 @@ using namespace tvz;
 struct tvz_catalog {
     int device = 0;
     long long n_rows = 0, n_vals = 0, n_pairs = 0;
+    long long n_pairs_padded = 0;  // ts is padded with a NaN pattern to whole count-kernel chunks
     unsigned long long *d_ts = nullptr;
     long long *d_off = nullptr;
     int *d_vid = nullptr;
+    int *d_block_row = nullptr;    // row holding stored value b*1024 (coarse index for hit -> row)
 };
 
 struct tvz_match_ws {
@@ -338,7 +365,18 @@ int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *
     c->n_rows = n_rows;
     c->n_vals = static_cast<long long>(ts.size());
     c->n_pairs = (c->n_vals + 1) / 2;
-    while (static_cast<long long>(ts.size()) < 2 * c->n_pairs + 2) ts.push_back(kPadPattern);
+    c->n_pairs_padded = (c->n_pairs + kChunkPairs - 1) / kChunkPairs * kChunkPairs;
+    ts.resize(static_cast<size_t>(2 * c->n_pairs_padded), kPadPattern);
+    // coarse index: last row whose offset is <= b*1024 (clamped to the last row)
+    std::vector<int> block_row(static_cast<size_t>((2 * c->n_pairs_padded) >> kBlockShift) + 2, 0);
+    {
+        long long r = 0;
+        for (size_t b = 0; b < block_row.size(); ++b) {
+            const long long e = static_cast<long long>(b) << kBlockShift;
+            while (r + 1 < n_rows && off[r + 1] <= e) ++r;
+            block_row[b] = static_cast<int>(r);
+        }
+    }
     cudaGetDevice(&c->device);
     auto fail = [&](cudaError_t e, const char *what) {
         set_error(TVZ_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
@@ -349,6 +387,10 @@ int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *
     if ((e = cudaMalloc(&c->d_ts, ts.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(ts)");
     if ((e = cudaMalloc(&c->d_off, off.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(off)");
     if ((e = cudaMalloc(&c->d_vid, std::max<size_t>(1, n_rows) * 4)) != cudaSuccess) return fail(e, "cudaMalloc(vid)");
+    if ((e = cudaMalloc(&c->d_block_row, block_row.size() * 4)) != cudaSuccess) return fail(e, "cudaMalloc(block_row)");
+    if ((e = cudaMemcpy(c->d_block_row, block_row.data(), block_row.size() * 4, cudaMemcpyHostToDevice)) !=
+        cudaSuccess)
+        return fail(e, "cudaMemcpy(block_row)");
     if ((e = cudaMemcpy(c->d_ts, ts.data(), ts.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail(e, "cudaMemcpy(ts)");
     if ((e = cudaMemcpy(c->d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
@@ -364,6 +406,7 @@ void tvz_catalog_destroy(tvz_catalog *c) {
     if (c->d_ts) cudaFree(c->d_ts);
     if (c->d_off) cudaFree(c->d_off);
     if (c->d_vid) cudaFree(c->d_vid);
+    if (c->d_block_row) cudaFree(c->d_block_row);
     delete c;
 }
 
@@ -479,16 +522,17 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
         TVZ_CUDA(cudaMemcpyAsync(ws->d_qcanon, h_qc, sizeof(unsigned long long) * qn, cudaMemcpyHostToDevice, st));
     if (cat->n_rows > 0) {
         const int sms = num_sms();
-        const long long chunk = static_cast<long long>(kCountThreads) * kCountUnroll;
-        const long long want = (cat->n_pairs + chunk - 1) / chunk;
-        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, 4ll * sms)));
+        TVZ_CUDA(cudaFuncSetAttribute(match_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(sizeof(CountSmem))));
+        const long long chunks = cat->n_pairs_padded / kChunkPairs;
+        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, 2ll * sms)));
         for (int k0 = 0; k0 < nk; k0 += kMaxKeys) {
             const int n = std::min(kMaxKeys, nk - k0);
             TVZ_CUDA(cudaMemcpyAsync(ws->d_keys, h_keys + k0, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, st));
             TVZ_CUDA(cudaMemcpyAsync(ws->d_mult, h_mult + k0, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-            match_count_kernel<<<grid, kCountThreads, 0, st>>>(reinterpret_cast<const ulonglong2 *>(cat->d_ts),
-                                                               cat->n_pairs, ws->d_keys, ws->d_mult, n, cat->d_off,
-                                                               cat->n_rows, ws->d_counts);
+            match_count_kernel<<<grid, kCountThreads, sizeof(CountSmem), st>>>(
+                reinterpret_cast<const ulonglong2 *>(cat->d_ts), cat->n_pairs_padded, ws->d_keys, ws->d_mult, n,
+                cat->d_off, cat->d_block_row, cat->n_rows, ws->d_counts);
             TVZ_CUDA(cudaGetLastError());
         }
         match_scan_kernel<<<ws->n_blocks, kScanThreads, 0, st>>>(ws->d_counts, cat->n_rows, min_match,
