@@ -31,7 +31,9 @@ SYMBOLS = [
     ("tvz_match_ws_counts", _vp, [_vp]),
 ]
 # debug hooks outside the public header
-_DEBUG_SYMBOLS = [("tvz_debug_sad_tuning", _i, [_i, _i, _i, _i])]
+_DEBUG_SYMBOLS = [("tvz_debug_sad_tuning", _i, [_i, _i, _i, _i]),
+                  ("tvz_debug_match_timing", _i, [_vp, _i]),
+                  ("tvz_debug_match_count_ms", _i, [_vp, C.POINTER(C.c_float)])]
 
 TVZ_ERR_OVERFLOW = -4
 _lib = None

@@ -123,6 +123,17 @@ class Catalogue:
             check(lib().tvz_catalog_match_async(self._handle, ws, q.ctypes.data, q.shape[0], int(min_match),
                                                 out.data_ptr(), cap, int(st.cuda_stream)))
 
+    def debug_count_kernel_ms(self, enable: bool | None = None) -> float | None:
+        """Bench hook: enable event timing of the count kernel on this thread's workspace, or
+        (enable=None) read the duration of the last query's count kernel in ms."""
+        ws = self._ws(0)
+        if enable is not None:
+            check(lib().tvz_debug_match_timing(ws, int(enable)))
+            return None
+        ms = C.c_float(0)
+        check(lib().tvz_debug_match_count_ms(ws, C.byref(ms)))
+        return float(ms.value)
+
     def find_duplicates(self, new_timestamps, min_match: int = 5) -> list[tuple[int, int]]:
         """db.py:76-94: list of (video_id, match_count) tuples of Python ints."""
         vid, cnt = self.match(new_timestamps, min_match)

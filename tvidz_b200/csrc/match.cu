@@ -30,8 +30,9 @@ constexpr int kMaxKeys = 2048;               // distinct query values per launch
 constexpr int kCountThreads = 512;
 constexpr int kCountUnroll = 4;              // 4 x 16 B in flight per thread
 constexpr int kChunkPairs = kCountThreads * kCountUnroll;  // 2048 pairs = 4096 values per CTA iteration
-constexpr int kQueueCap = 1024;              // filter survivors parked per iteration
-constexpr int kBlockShift = 10;              // coarse row index: one entry per 1024 stored values
+constexpr int kCountWarps = kCountThreads / 32;
+constexpr int kWarpQueue = 64;               // filter survivors parked per warp
+constexpr int kBlockShift = 8;               // coarse row index: one entry per 256 stored values
 constexpr int kScanThreads = 256;
 constexpr int kScanRowsPerThread = 8;
 constexpr int kScanRowsPerBlock = kScanThreads * kScanRowsPerThread;
@@ -40,10 +41,9 @@ constexpr unsigned long long kPadPattern = 0x7ff8dead0000beefull;  // a NaN: nev
 struct alignas(16) CountSmem {
     unsigned char map[kMapEntries];   // first: zeroed with 16-byte stores
     unsigned long long keys[kMaxKeys];
-    unsigned long long qv[kQueueCap];
+    unsigned long long qv[kCountWarps][kWarpQueue];
+    long long qe[kCountWarps][kWarpQueue];
     int mult[kMaxKeys];
-    unsigned qo[kQueueCap];
-    unsigned qcount[2];
 };
 
 // Two IMADs and a shift: good enough on frame-quantised timestamps and on x.0 / x.5 values
@@ -56,10 +56,12 @@ __host__ __device__ __forceinline__ uint32_t filter_hash(unsigned long long v) {
 // counts[row] += mult(v) for every stored value v that equals a query value.
 //
 // Streaming pass over `ts` (padded to whole chunks, so the hot loop has no bounds checks):
-// per value one hash, one LDS.U8 and a branch.  Survivors (true matches plus ~0.1% false
-// positives) are parked in a shared-memory queue and resolved after the chunk by all threads
-// together -- exact key lookup, then the row through a coarse index (row of every 1024th
-// value) and a short search in `off` -- so a hit never stalls the other 31 lanes of its warp.
+// per value one hash, one LDS.U8 and a warp vote; the next chunk's 128-bit loads are already
+// in flight while the current one is probed.  Survivors (true matches plus ~0.1% false
+// positives) are parked in a per-warp shared-memory queue -- slots handed out from the vote
+// mask, no atomics -- and resolved 32 at a time by the whole warp: exact key lookup, then the
+// row through a coarse index (row of every 256th value) and a short search in `off`.  A hit
+// therefore never stalls the other 31 lanes, and no CTA-wide barrier sits in the loop.
 __global__ void __launch_bounds__(kCountThreads, 2)
 match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
                    const unsigned long long *__restrict__ keys, const int *__restrict__ mult, int n_keys,
@@ -69,7 +71,6 @@ match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
     CountSmem &sm = *reinterpret_cast<CountSmem *>(smem_raw);
     for (int i = threadIdx.x; i < kMapEntries / 16; i += kCountThreads)
         reinterpret_cast<uint4 *>(sm.map)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x < 2) sm.qcount[threadIdx.x] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < n_keys; i += kCountThreads) {
         const unsigned long long k = keys[i];
@@ -78,6 +79,11 @@ match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
         sm.map[filter_hash(k)] = 1;
     }
     __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    unsigned long long *qv = sm.qv[threadIdx.x >> 5];
+    long long *qe = sm.qe[threadIdx.x >> 5];
+    int queued = 0;  // warp-uniform
 
     auto resolve = [&](unsigned long long v, long long elem) {
         int lo = 0, hi = n_keys;  // keys sorted ascending as uint64
@@ -94,34 +100,50 @@ match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
         }
         atomicAdd(&counts[a], sm.mult[lo]);
     };
-
-    unsigned it = 0;
-    for (long long base = static_cast<long long>(blockIdx.x) * kChunkPairs; base < n_pairs_padded;
-         base += static_cast<long long>(gridDim.x) * kChunkPairs, ++it) {
-        const ulonglong2 *src = ts2 + base + threadIdx.x;
-        ulonglong2 v[kCountUnroll];
-#pragma unroll
-        for (int j = 0; j < kCountUnroll; ++j) v[j] = __ldcs(src + j * kCountThreads);
-        unsigned *qc = &sm.qcount[it & 1];
-        auto probe = [&](unsigned long long x, unsigned rel) {
-            if (sm.map[filter_hash(x)]) {
-                const unsigned slot = atomicAdd(qc, 1u);
-                if (slot < kQueueCap) { sm.qv[slot] = x; sm.qo[slot] = rel; }
-                else resolve(x, 2 * base + rel);  // queue full (dense matches): resolve in place
+    auto drain = [&]() {
+        __syncwarp();
+        for (int i = lane; i < min(queued, kWarpQueue); i += 32) resolve(qv[i], qe[i]);
+        __syncwarp();
+        queued = 0;
+    };
+    auto probe = [&](unsigned long long x, long long elem) {
+        const bool pass = sm.map[filter_hash(x)] != 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+        if (mask) {
+            if (pass) {
+                const int slot = queued + __popc(mask & ((1u << lane) - 1u));
+                if (slot < kWarpQueue) { qv[slot] = x; qe[slot] = elem; }
+                else resolve(x, elem);  // queue full (dense matches): resolve in place
             }
-        };
+            queued += __popc(mask);
+        }
+    };
+
+    const long long stride = static_cast<long long>(gridDim.x) * kChunkPairs;
+    long long base = static_cast<long long>(blockIdx.x) * kChunkPairs;
+    ulonglong2 v[kCountUnroll], nv[kCountUnroll];
+    if (base < n_pairs_padded) {
+#pragma unroll
+        for (int j = 0; j < kCountUnroll; ++j) v[j] = __ldcs(ts2 + base + j * kCountThreads + threadIdx.x);
+    }
+    for (; base < n_pairs_padded; base += stride) {
+        const bool more = base + stride < n_pairs_padded;
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < kCountUnroll; ++j)
+                nv[j] = __ldcs(ts2 + base + stride + j * kCountThreads + threadIdx.x);
+        }
 #pragma unroll
         for (int j = 0; j < kCountUnroll; ++j) {
-            const unsigned rel = 2u * (j * kCountThreads + threadIdx.x);
-            probe(v[j].x, rel);
-            probe(v[j].y, rel + 1u);
+            const long long elem = 2 * (base + j * kCountThreads + threadIdx.x);
+            probe(v[j].x, elem);
+            probe(v[j].y, elem + 1);
         }
-        __syncthreads();
-        const unsigned n = min(*qc, static_cast<unsigned>(kQueueCap));
-        if (threadIdx.x == 0) sm.qcount[(it + 1) & 1] = 0;
-        for (unsigned i = threadIdx.x; i < n; i += kCountThreads) resolve(sm.qv[i], 2 * base + sm.qo[i]);
-        __syncthreads();
+        if (queued >= kWarpQueue / 2) drain();
+#pragma unroll
+        for (int j = 0; j < kCountUnroll; ++j) v[j] = nv[j];
     }
+    drain();
 }
 
 // Ordered compaction, pass 1: qualifying rows per block of kScanRowsPerBlock rows.
@@ -287,6 +309,8 @@ struct tvz_match_ws {
     cudaStream_t stream = nullptr; // private stream for the synchronous entry point
     cudaEvent_t staged = nullptr;  // the pinned staging buffer has been consumed
     bool stage_busy = false;
+    bool timing = false;           // debug: bracket the count kernel(s) with events
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
 namespace {
@@ -472,6 +496,8 @@ void tvz_match_ws_destroy(tvz_match_ws *ws) {
     if (ws->h_out) cudaFreeHost(ws->h_out);
     if (ws->h_kth) cudaFreeHost(ws->h_kth);
     if (ws->staged) cudaEventDestroy(ws->staged);
+    if (ws->t0) cudaEventDestroy(ws->t0);
+    if (ws->t1) cudaEventDestroy(ws->t1);
     if (ws->stream) cudaStreamDestroy(ws->stream);
     delete ws;
 }
@@ -530,11 +556,13 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
             const int n = std::min(kMaxKeys, nk - k0);
             TVZ_CUDA(cudaMemcpyAsync(ws->d_keys, h_keys + k0, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, st));
             TVZ_CUDA(cudaMemcpyAsync(ws->d_mult, h_mult + k0, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+            if (ws->timing && k0 == 0) TVZ_CUDA(cudaEventRecord(ws->t0, st));
             match_count_kernel<<<grid, kCountThreads, sizeof(CountSmem), st>>>(
                 reinterpret_cast<const ulonglong2 *>(cat->d_ts), cat->n_pairs_padded, ws->d_keys, ws->d_mult, n,
                 cat->d_off, cat->d_block_row, cat->n_rows, ws->d_counts);
             TVZ_CUDA(cudaGetLastError());
         }
+        if (ws->timing && nk > 0) TVZ_CUDA(cudaEventRecord(ws->t1, st));
         match_scan_kernel<<<ws->n_blocks, kScanThreads, 0, st>>>(ws->d_counts, cat->n_rows, min_match,
                                                                  ws->d_block_hits);
         TVZ_CUDA(cudaGetLastError());
@@ -559,6 +587,24 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
 }  // namespace
 
 extern "C" {
+
+// Debug hooks (not in the public header): time the count kernel of the last query with CUDA
+// events recorded on the query's own stream.
+int tvz_debug_match_timing(tvz_match_ws *ws, int enable) {
+    TVZ_REQUIRE(ws, "null workspace");
+    if (enable && !ws->t0) {
+        TVZ_CUDA(cudaEventCreate(&ws->t0));
+        TVZ_CUDA(cudaEventCreate(&ws->t1));
+    }
+    ws->timing = enable != 0;
+    return TVZ_OK;
+}
+int tvz_debug_match_count_ms(tvz_match_ws *ws, float *ms) {
+    TVZ_REQUIRE(ws && ms && ws->t0, "timing was never enabled");
+    TVZ_CUDA(cudaEventSynchronize(ws->t1));
+    TVZ_CUDA(cudaEventElapsedTime(ms, ws->t0, ws->t1));
+    return TVZ_OK;
+}
 
 int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match,
                             int32_t *d_out, int64_t out_cap, void *stream) {
