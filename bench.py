@@ -97,14 +97,23 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arms (oracle = test infrastructure)
+def host_threads() -> int:
+    """All the host threads this process may use (torchrun pins OMP_NUM_THREADS=1: ask the OS)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_scoring_baseline(frames_np: np.ndarray, budget_s: float = 10.0):
     """The C restatement of FFmpeg's scene score on all host cores, one stream per thread."""
     import oracle
     S, F = frames_np.shape[:2]
-    oracle.scene_batch(np.ascontiguousarray(frames_np[: min(S, 8), : min(F, 4)]))            # warm (page-in, thread pool)
+    nt = host_threads()
+    oracle.scene_batch(np.ascontiguousarray(frames_np[: min(S, 8), : min(F, 4)]), n_threads=nt)   # warm
     done, t0, used = 0, time.perf_counter(), 1
     while True:
-        _, _, _, used = oracle.scene_batch(frames_np)
+        _, _, _, used = oracle.scene_batch(frames_np, n_threads=nt)
         done += S * (F - 1)
         el = time.perf_counter() - t0
         if el >= budget_s or done >= 40 * S * (F - 1):
@@ -155,12 +164,13 @@ def run_reference(args):
     S, F = N_STREAMS, 5                                   # bounded sample: 64 streams x 5 frames per step
     frames = make_host_frames(S, F, seed=1)
     import oracle
+    nt = host_threads()
     for _ in range(max(args.warmup, 1)):
-        oracle.scene_batch(frames)
+        oracle.scene_batch(frames, n_threads=nt)
     t0 = time.perf_counter()
     used = 1
     for _ in range(args.steps):
-        _, _, _, used = oracle.scene_batch(frames)
+        _, _, _, used = oracle.scene_batch(frames, n_threads=nt)
     el = time.perf_counter() - t0
     value = args.steps * S * (F - 1) / el
     from tvidz_b200 import synth

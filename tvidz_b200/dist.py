@@ -96,5 +96,5 @@ class ShardedCatalogue:
             pairs, overflow, needed = merge_records(
                 self.gathered.view(self.world, self.cap + 1, 2).cpu().numpy(), self.cap)
             if not overflow:
-                return [(int(v), int(c)) for v, c in pairs]
+                return list(zip(pairs[:, 0].tolist(), pairs[:, 1].tolist()))
             self._alloc(max(needed, 2 * self.cap))     # every rank sees the same records -> same decision
