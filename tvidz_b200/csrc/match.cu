@@ -62,20 +62,29 @@ __host__ __device__ __forceinline__ uint32_t filter_hash(unsigned long long v) {
 // mask, no atomics -- and resolved 32 at a time by the whole warp: exact key lookup, then the
 // row through a coarse index (row of every 256th value) and a short search in `off`.  A hit
 // therefore never stalls the other 31 lanes, and no CTA-wide barrier sits in the loop.
+// Short queries (the common case: a video has tens of cuts) ride in the kernel parameters,
+// which saves the two host->device copies in front of the launch.
+constexpr int kParamKeys = 224;
+struct SmallQuery {
+    unsigned long long keys[kParamKeys];
+    int mult[kParamKeys];
+};
+
+template <bool kParamQuery>
 __global__ void __launch_bounds__(kCountThreads, 2)
 match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
                    const unsigned long long *__restrict__ keys, const int *__restrict__ mult, int n_keys,
                    const long long *__restrict__ off, const int *__restrict__ block_row, long long n_rows,
-                   int *__restrict__ counts) {
+                   int *__restrict__ counts, const __grid_constant__ SmallQuery sq) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CountSmem &sm = *reinterpret_cast<CountSmem *>(smem_raw);
     for (int i = threadIdx.x; i < kMapEntries / 16; i += kCountThreads)
         reinterpret_cast<uint4 *>(sm.map)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     for (int i = threadIdx.x; i < n_keys; i += kCountThreads) {
-        const unsigned long long k = keys[i];
+        const unsigned long long k = kParamQuery ? sq.keys[i] : keys[i];
         sm.keys[i] = k;
-        sm.mult[i] = mult[i];
+        sm.mult[i] = kParamQuery ? sq.mult[i] : mult[i];
         sm.map[filter_hash(k)] = 1;
     }
     __syncthreads();
@@ -146,64 +155,45 @@ match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
     drain();
 }
 
-// Ordered compaction, pass 1: qualifying rows per block of kScanRowsPerBlock rows.
-__global__ void __launch_bounds__(kScanThreads)
-match_scan_kernel(const int *__restrict__ counts, long long n_rows, int min_match, int *__restrict__ block_hits) {
-    const long long r0 = blockIdx.x * static_cast<long long>(kScanRowsPerBlock) + threadIdx.x * kScanRowsPerThread;
-    int c = 0;
-#pragma unroll
-    for (int j = 0; j < kScanRowsPerThread; ++j)
-        if (r0 + j < n_rows && counts[r0 + j] >= min_match) ++c;
-    c = __reduce_add_sync(0xffffffffu, c);
-    __shared__ int ws[kScanThreads / 32];
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int i = 0; i < kScanThreads / 32; ++i) t += ws[i];
-        block_hits[blockIdx.x] = t;
-    }
+// Ordered compaction of the rows with counts[row] >= min_match, in ONE pass (decoupled
+// look-back): a block takes a ticket (so tickets start in order), counts its qualifying rows,
+// publishes {epoch, AGGREGATE, n}, sums its predecessors' records walking backwards 32 at a
+// time until it meets an inclusive PREFIX, publishes its own PREFIX, and writes its rows at
+// that offset in row order; counts[] is zeroed for the next query.  Records carry the query
+// epoch, so `state` never needs clearing.  out: int32 [cap+1][2]; out[0] = {n_hits saturated,
+// overflow flag}; out[1+h] = {video_id, match_count}; rows_out[h] = row index.
+constexpr unsigned long long kStateAggregate = 1ull << 32, kStatePrefix = 2ull << 32;
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Pass 2: each block sums the block_hits before it, then writes its qualifying rows in row
-// order and zeroes counts[] for the next query.  out: int32 [cap+1][2]; out[0] = {n_hits
-// (saturated), overflow flag}; out[1+h] = {video_id, match_count}.  rows_out[h] = row index.
 __global__ void __launch_bounds__(kScanThreads)
-match_emit_kernel(int *__restrict__ counts, long long n_rows, int min_match, const int *__restrict__ block_hits,
-                  int n_blocks, const int *__restrict__ vid, int *__restrict__ out, long long *__restrict__ rows_out,
-                  long long cap, long long *__restrict__ n_hits_out) {
-    __shared__ long long s_base;
+match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, const int *__restrict__ vid,
+                     int *__restrict__ out, long long *__restrict__ rows_out, long long cap,
+                     long long *__restrict__ n_hits_out, unsigned long long *state, unsigned *ticket) {
+    // ticket[0] = next ticket, ticket[1] = query epoch.  The epoch is read BEFORE the ticket is
+    // taken and bumped by the holder of the last ticket, i.e. after every block has read it:
+    // the kernel is self-contained and can be replayed from a CUDA graph.
+    __shared__ unsigned s_block, s_epoch;
+    __shared__ long long s_excl;
     __shared__ int ws[kScanThreads / 32];
-    // exclusive prefix over earlier blocks (+ grand total for the header, block 0 only)
-    long long before = 0, total = 0;
-    for (int i = threadIdx.x; i < n_blocks; i += kScanThreads) {
-        const int h = block_hits[i];
-        if (i < static_cast<int>(blockIdx.x)) before += h;
-        total += h;
+    if (threadIdx.x == 0) {
+        unsigned e;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(ticket + 1) : "memory");
+        s_epoch = e;
+        s_block = atomicAdd(ticket, 1u);
     }
-    // block-wide sums of two 64-bit values
-    auto block_sum = [&](long long v) {
-        unsigned lo = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(v & 0xffff));
-        unsigned hi = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(v >> 16));  // per-thread v < 2^47
-        long long w = (static_cast<long long>(hi) << 16) + lo;
-        __shared__ long long acc[kScanThreads / 32];
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) acc[threadIdx.x >> 5] = w;
-        __syncthreads();
-        long long t = 0;
-        for (int i = 0; i < kScanThreads / 32; ++i) t += acc[i];
-        return t;
-    };
-    before = block_sum(before);
-    if (blockIdx.x == 0) {
-        total = block_sum(total);
-        if (threadIdx.x == 0) {
-            *n_hits_out = total;
-            out[0] = total > 0x7fffffffll ? 0x7fffffff : static_cast<int>(total);
-            out[1] = total > cap ? 1 : 0;
-        }
-    }
-    const long long r0 = blockIdx.x * static_cast<long long>(kScanRowsPerBlock) + threadIdx.x * kScanRowsPerThread;
+    __syncthreads();
+    const unsigned blk = s_block;
+    const unsigned epoch = s_epoch;
+    const unsigned long long tag = static_cast<unsigned long long>(epoch) << 34;
+    const long long r0 = blk * static_cast<long long>(kScanRowsPerBlock) + threadIdx.x * kScanRowsPerThread;
     int cnt[kScanRowsPerThread];
     int mine = 0;
 #pragma unroll
@@ -215,7 +205,7 @@ match_emit_kernel(int *__restrict__ counts, long long n_rows, int min_match, con
             if (c >= min_match) { cnt[j] = c; ++mine; }
         }
     }
-    // exclusive scan of `mine` across the block (rows are thread-contiguous, so thread order = row order)
+    // block-wide exclusive scan of `mine` (rows are thread-contiguous: thread order = row order)
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -224,13 +214,62 @@ match_emit_kernel(int *__restrict__ counts, long long n_rows, int min_match, con
     }
     if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int i = 0; i < kScanThreads / 32; ++i) { const int t = ws[i]; ws[i] = run; run += t; }
-        s_base = before;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int w = lane < kScanThreads / 32 ? ws[lane] : 0;
+        int run = w;
+#pragma unroll
+        for (int d = 1; d < kScanThreads / 32; d <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, run, d);
+            if (lane >= d) run += n;
+        }
+        if (lane < kScanThreads / 32) ws[lane] = run - w;  // exclusive warp offsets
+        const unsigned agg = static_cast<unsigned>(__shfl_sync(0xffffffffu, run, kScanThreads / 32 - 1));
+        long long excl = 0;
+        if (blk == 0) {
+            if (lane == 0) st_release_u64(&state[0], tag | kStatePrefix | agg);
+        } else {
+            if (lane == 0) st_release_u64(&state[blk], tag | kStateAggregate | agg);
+            long long idx = static_cast<long long>(blk) - 1;
+            while (true) {
+                const long long i = idx - lane;
+                unsigned long long rec = 0;
+                unsigned prefix_mask, valid_mask;
+                do {  // poll until the window up to the first PREFIX is published for this epoch
+                    rec = i >= 0 ? ld_acquire_u64(&state[i]) : (tag | kStatePrefix);
+                    const bool ok = (rec >> 34) == epoch && ((rec >> 32) & 3ull) != 0;
+                    valid_mask = __ballot_sync(0xffffffffu, ok);
+                    prefix_mask = __ballot_sync(0xffffffffu, ok && ((rec >> 32) & 3ull) == 2ull);
+                    // lanes below the first PREFIX lane must all be valid
+                } while ((prefix_mask ? ((valid_mask | ~((prefix_mask & -prefix_mask) - 1u)) != 0xffffffffu)
+                                      : (valid_mask != 0xffffffffu)));
+                const unsigned upto = prefix_mask ? (prefix_mask & -prefix_mask) : 0u;
+                const unsigned take = prefix_mask ? ((upto - 1u) | upto) : 0xffffffffu;  // lanes 0..first PREFIX
+                long long v = ((take >> lane) & 1u) ? static_cast<long long>(rec & 0xffffffffull) : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (prefix_mask) break;
+                idx -= 32;
+            }
+            // hits are bounded by rows < 2^32 per shard, so the running prefix fits 32 bits
+            if (lane == 0) st_release_u64(&state[blk], tag | kStatePrefix | static_cast<unsigned>(excl + agg));
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (blk == gridDim.x - 1) {  // last ticket: every block has its ticket, totals are final
+                const long long total = excl + agg;
+                *n_hits_out = total;
+                out[0] = total > 0x7fffffffll ? 0x7fffffff : static_cast<int>(total);
+                out[1] = total > cap ? 1 : 0;
+                ticket[1] = (epoch + 1u) & 0x3fffffffu;  // every record is rewritten per query: no stale match
+                __threadfence();
+                ticket[0] = 0;
+            }
+        }
     }
     __syncthreads();
-    long long pos = s_base + ws[threadIdx.x >> 5] + (incl - mine);
+    long long pos = s_excl + ws[threadIdx.x >> 5] + (incl - mine);
 #pragma unroll
     for (int j = 0; j < kScanRowsPerThread; ++j) {
         if (cnt[j] >= 0) {
@@ -293,7 +332,8 @@ struct tvz_match_ws {
     long long cap = 0;
     int n_blocks = 0;
     int *d_counts = nullptr;       // [n_rows], zero between queries
-    int *d_block_hits = nullptr;   // [n_blocks]
+    unsigned long long *d_state = nullptr;  // [n_blocks] look-back records {epoch, flag, value}
+    unsigned *d_ticket = nullptr;           // {next ticket, query epoch}
     int *d_out = nullptr;          // [cap+1][2]
     long long *d_rows = nullptr;   // [cap]
     int *d_kth = nullptr;          // [cap]
@@ -455,7 +495,14 @@ int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_
     const size_t nr = std::max<long long>(1, cat->n_rows);
     if ((e = cudaMalloc(&ws->d_counts, nr * 4)) != cudaSuccess) return bail(e, "cudaMalloc(counts)");
     if ((e = cudaMemset(ws->d_counts, 0, nr * 4)) != cudaSuccess) return bail(e, "cudaMemset(counts)");
-    if ((e = cudaMalloc(&ws->d_block_hits, std::max(1, ws->n_blocks) * 4)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ws->d_state, std::max(1, ws->n_blocks) * 8)) != cudaSuccess) return bail(e, "cudaMalloc(state)");
+    if ((e = cudaMemset(ws->d_state, 0, std::max(1, ws->n_blocks) * 8)) != cudaSuccess) return bail(e, "cudaMemset(state)");
+    if ((e = cudaMalloc(&ws->d_ticket, 8)) != cudaSuccess) return bail(e, "cudaMalloc(ticket)");
+    {
+        const unsigned init[2] = {0u, 1u};
+        if ((e = cudaMemcpy(ws->d_ticket, init, 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+            return bail(e, "cudaMemcpy(ticket)");
+    }
     if ((e = cudaMalloc(&ws->d_out, (ws->cap + 1) * 8)) != cudaSuccess) return bail(e, "cudaMalloc(out)");
     if ((e = cudaMemset(ws->d_out, 0, 8)) != cudaSuccess) return bail(e, "cudaMemset(out)");
     if ((e = cudaMalloc(&ws->d_rows, ws->cap * 8)) != cudaSuccess) return bail(e, "cudaMalloc(rows)");
@@ -484,7 +531,8 @@ void tvz_match_ws_destroy(tvz_match_ws *ws) {
     if (!ws) return;
     if (ws->stream) cudaStreamSynchronize(ws->stream);
     if (ws->d_counts) cudaFree(ws->d_counts);
-    if (ws->d_block_hits) cudaFree(ws->d_block_hits);
+    if (ws->d_state) cudaFree(ws->d_state);
+    if (ws->d_ticket) cudaFree(ws->d_ticket);
     if (ws->d_out) cudaFree(ws->d_out);
     if (ws->d_rows) cudaFree(ws->d_rows);
     if (ws->d_kth) cudaFree(ws->d_kth);
@@ -548,27 +596,40 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
         TVZ_CUDA(cudaMemcpyAsync(ws->d_qcanon, h_qc, sizeof(unsigned long long) * qn, cudaMemcpyHostToDevice, st));
     if (cat->n_rows > 0) {
         const int sms = num_sms();
-        TVZ_CUDA(cudaFuncSetAttribute(match_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(sizeof(CountSmem))));
         const long long chunks = cat->n_pairs_padded / kChunkPairs;
         const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, 2ll * sms)));
-        for (int k0 = 0; k0 < nk; k0 += kMaxKeys) {
-            const int n = std::min(kMaxKeys, nk - k0);
-            TVZ_CUDA(cudaMemcpyAsync(ws->d_keys, h_keys + k0, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, st));
-            TVZ_CUDA(cudaMemcpyAsync(ws->d_mult, h_mult + k0, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-            if (ws->timing && k0 == 0) TVZ_CUDA(cudaEventRecord(ws->t0, st));
-            match_count_kernel<<<grid, kCountThreads, sizeof(CountSmem), st>>>(
-                reinterpret_cast<const ulonglong2 *>(cat->d_ts), cat->n_pairs_padded, ws->d_keys, ws->d_mult, n,
-                cat->d_off, cat->d_block_row, cat->n_rows, ws->d_counts);
-            TVZ_CUDA(cudaGetLastError());
+        const ulonglong2 *ts2 = reinterpret_cast<const ulonglong2 *>(cat->d_ts);
+        if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
+        if (nk <= kParamKeys) {
+            SmallQuery sq;
+            memcpy(sq.keys, h_keys, sizeof(unsigned long long) * nk);
+            memcpy(sq.mult, h_mult, sizeof(int) * nk);
+            TVZ_CUDA(cudaFuncSetAttribute(match_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(sizeof(CountSmem))));
+            if (nk > 0) {
+                match_count_kernel<true><<<grid, kCountThreads, sizeof(CountSmem), st>>>(
+                    ts2, cat->n_pairs_padded, nullptr, nullptr, nk, cat->d_off, cat->d_block_row, cat->n_rows,
+                    ws->d_counts, sq);
+                TVZ_CUDA(cudaGetLastError());
+            }
+        } else {
+            TVZ_CUDA(cudaFuncSetAttribute(match_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(sizeof(CountSmem))));
+            for (int k0 = 0; k0 < nk; k0 += kMaxKeys) {
+                const int n = std::min(kMaxKeys, nk - k0);
+                TVZ_CUDA(cudaMemcpyAsync(ws->d_keys, h_keys + k0, sizeof(unsigned long long) * n,
+                                         cudaMemcpyHostToDevice, st));
+                TVZ_CUDA(cudaMemcpyAsync(ws->d_mult, h_mult + k0, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+                match_count_kernel<false><<<grid, kCountThreads, sizeof(CountSmem), st>>>(
+                    ts2, cat->n_pairs_padded, ws->d_keys, ws->d_mult, n, cat->d_off, cat->d_block_row, cat->n_rows,
+                    ws->d_counts, SmallQuery{});
+                TVZ_CUDA(cudaGetLastError());
+            }
         }
-        if (ws->timing && nk > 0) TVZ_CUDA(cudaEventRecord(ws->t1, st));
-        match_scan_kernel<<<ws->n_blocks, kScanThreads, 0, st>>>(ws->d_counts, cat->n_rows, min_match,
-                                                                 ws->d_block_hits);
-        TVZ_CUDA(cudaGetLastError());
-        match_emit_kernel<<<ws->n_blocks, kScanThreads, 0, st>>>(ws->d_counts, cat->n_rows, min_match,
-                                                                 ws->d_block_hits, ws->n_blocks, cat->d_vid, d_out,
-                                                                 ws->d_rows, out_cap, ws->d_nhits);
+        if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
+        match_compact_kernel<<<ws->n_blocks, kScanThreads, 0, st>>>(ws->d_counts, cat->n_rows, min_match, cat->d_vid,
+                                                                    d_out, ws->d_rows, out_cap, ws->d_nhits,
+                                                                    ws->d_state, ws->d_ticket);
         TVZ_CUDA(cudaGetLastError());
         if (want_kth) {
             match_kth_kernel<<<2 * sms, 256, 0, st>>>(cat->d_ts, cat->d_off, ws->d_rows, d_out, out_cap,
