@@ -55,8 +55,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+// try_wait suspends for a hardware-chosen interval, so 2^26 polls are many seconds.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
+    unsigned polls = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++polls == (1u << 26)) {
+#ifdef TVZ_DEBUG_WAIT
+            printf("tvidz_b200: mbarrier wait timed out (tag %d, block %d, thread %d, bar 0x%x, parity %u)\n", tag,
+                   (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+#endif
+            (void)tag;
+            __trap();
+        }
     }
 }
 // TMA 1-D bulk copy global -> shared::cta, completion reported on an mbarrier (SASS: UBLKCP).

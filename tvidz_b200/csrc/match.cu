@@ -13,9 +13,9 @@
 //     vid  : int32 [n_rows]   videos.id of each row
 // Because in-row repeats are gone, match_count(row) = sum over stored values v of
 // mult(v), where mult(v) = number of query positions equal to v.  The count kernel is
-// therefore a pure streaming pass over `ts` (the only large array): 128-bit coalesced
-// loads, a shared-memory Bloom bitmap of the query rejects ~all values with one LDS, and
-// the rare survivors are looked up exactly and added to counts[row] with a RED.
+// therefore a pure streaming pass over `ts` (the only large array): 256-bit coalesced
+// loads, a 64 KB shared-memory byte map of the query rejects ~all values with one LDS.U8,
+// and the rare survivors are looked up exactly and added to counts[row] with a RED.
 #include <algorithm>
 #include <unordered_set>
 #include <vector>
@@ -28,8 +28,8 @@ namespace {
 constexpr int kMapEntries = 1 << 16;         // byte-map filter of the query: 64 KB of shared memory
 constexpr int kMaxKeys = 2048;               // distinct query values per launch
 constexpr int kCountThreads = 512;
-constexpr int kCountUnroll = 4;              // 4 x 16 B in flight per thread
-constexpr int kChunkPairs = kCountThreads * kCountUnroll;  // 2048 pairs = 4096 values per CTA iteration
+constexpr int kCountUnroll = 8;              // 8 x 16 B (= 4 x 256-bit loads) in flight per thread
+constexpr int kChunkPairs = kCountThreads * kCountUnroll;  // 4096 pairs = 8192 values per CTA iteration
 constexpr int kCountWarps = kCountThreads / 32;
 constexpr int kWarpQueue = 64;               // filter survivors parked per warp
 constexpr int kBlockShift = 8;               // coarse row index: one entry per 256 stored values
@@ -69,6 +69,19 @@ struct SmallQuery {
     unsigned long long keys[kParamKeys];
     int mult[kParamKeys];
 };
+
+// 256-bit streaming load (sm_100 LDG.E.256): no L1 allocation -- this kernel leaves L1 almost
+// no room, shared memory takes ~213 of the SM's 228 KB -- and evict-first in L2.
+struct U64x4 {
+    unsigned long long a, b, c, d;
+};
+__device__ __forceinline__ U64x4 ld_stream_256(const void *p) {
+    U64x4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d)
+                 : "l"(p));
+    return r;
+}
 
 template <bool kParamQuery>
 __global__ void __launch_bounds__(kCountThreads, 2)
@@ -115,42 +128,48 @@ match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
         __syncwarp();
         queued = 0;
     };
-    auto probe = [&](unsigned long long x, long long elem) {
-        const bool pass = sm.map[filter_hash(x)] != 0;
+    // park the lanes whose value survived the filter (slots from the vote mask, no atomics)
+    auto park = [&](bool pass, unsigned long long x, long long elem) {
         const unsigned mask = __ballot_sync(0xffffffffu, pass);
-        if (mask) {
-            if (pass) {
-                const int slot = queued + __popc(mask & ((1u << lane) - 1u));
-                if (slot < kWarpQueue) { qv[slot] = x; qe[slot] = elem; }
-                else resolve(x, elem);  // queue full (dense matches): resolve in place
-            }
-            queued += __popc(mask);
+        if (pass) {
+            const int slot = queued + __popc(mask & ((1u << lane) - 1u));
+            if (slot < kWarpQueue) { qv[slot] = x; qe[slot] = elem; }
+            else resolve(x, elem);  // queue full (dense matches): resolve in place
         }
+        queued += __popc(mask);
     };
-
+    // A chunk = 4096 pairs = 2048 units of 32 bytes; thread t owns units t, t+512, t+1024, t+1536.
+    // Rolling prefetch: as soon as a unit has been probed its registers are reloaded from the
+    // next chunk, so ~4 x 32 B per thread stay in flight without a second register buffer.
+    constexpr int kUnits = kCountUnroll / 2;
     const long long stride = static_cast<long long>(gridDim.x) * kChunkPairs;
     long long base = static_cast<long long>(blockIdx.x) * kChunkPairs;
-    ulonglong2 v[kCountUnroll], nv[kCountUnroll];
+    const U64x4 *ts4 = reinterpret_cast<const U64x4 *>(ts2);
+    U64x4 v[kUnits];
     if (base < n_pairs_padded) {
 #pragma unroll
-        for (int j = 0; j < kCountUnroll; ++j) v[j] = __ldcs(ts2 + base + j * kCountThreads + threadIdx.x);
+        for (int j = 0; j < kUnits; ++j) v[j] = ld_stream_256(ts4 + (base >> 1) + j * kCountThreads + threadIdx.x);
     }
     for (; base < n_pairs_padded; base += stride) {
         const bool more = base + stride < n_pairs_padded;
-        if (more) {
+        const U64x4 *next = ts4 + ((base + stride) >> 1) + threadIdx.x;
 #pragma unroll
-            for (int j = 0; j < kCountUnroll; ++j)
-                nv[j] = __ldcs(ts2 + base + stride + j * kCountThreads + threadIdx.x);
-        }
-#pragma unroll
-        for (int j = 0; j < kCountUnroll; ++j) {
-            const long long elem = 2 * (base + j * kCountThreads + threadIdx.x);
-            probe(v[j].x, elem);
-            probe(v[j].y, elem + 1);
+        for (int j = 0; j < kUnits; ++j) {
+            unsigned m4 = static_cast<unsigned>(sm.map[filter_hash(v[j].a)]);
+            m4 |= static_cast<unsigned>(sm.map[filter_hash(v[j].b)]) << 1;
+            m4 |= static_cast<unsigned>(sm.map[filter_hash(v[j].c)]) << 2;
+            m4 |= static_cast<unsigned>(sm.map[filter_hash(v[j].d)]) << 3;
+            const unsigned any = __reduce_or_sync(0xffffffffu, m4);  // did any of the warp's 128 values survive?
+            if (any) {
+                const long long elem = 2 * base + 4 * (j * kCountThreads + threadIdx.x);
+                if (any & 1u) park(m4 & 1u, v[j].a, elem);
+                if (any & 2u) park((m4 >> 1) & 1u, v[j].b, elem + 1);
+                if (any & 4u) park((m4 >> 2) & 1u, v[j].c, elem + 2);
+                if (any & 8u) park((m4 >> 3) & 1u, v[j].d, elem + 3);
+            }
+            if (more) v[j] = ld_stream_256(next + j * kCountThreads);
         }
         if (queued >= kWarpQueue / 2) drain();
-#pragma unroll
-        for (int j = 0; j < kCountUnroll; ++j) v[j] = nv[j];
     }
     drain();
 }
@@ -600,30 +619,31 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
         const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, 2ll * sms)));
         const ulonglong2 *ts2 = reinterpret_cast<const ulonglong2 *>(cat->d_ts);
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
+        auto launch = [&](bool param, const unsigned long long *dk, const int *dm, int n, const SmallQuery &sq) -> int {
+            auto kern = param ? match_count_kernel<true> : match_count_kernel<false>;
+            TVZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(sizeof(CountSmem))));
+            kern<<<grid, kCountThreads, sizeof(CountSmem), st>>>(ts2, cat->n_pairs_padded, dk, dm, n, cat->d_off,
+                                                                 cat->d_block_row, cat->n_rows, ws->d_counts, sq);
+            TVZ_CUDA(cudaGetLastError());
+            return TVZ_OK;
+        };
         if (nk <= kParamKeys) {
             SmallQuery sq;
             memcpy(sq.keys, h_keys, sizeof(unsigned long long) * nk);
             memcpy(sq.mult, h_mult, sizeof(int) * nk);
-            TVZ_CUDA(cudaFuncSetAttribute(match_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(sizeof(CountSmem))));
             if (nk > 0) {
-                match_count_kernel<true><<<grid, kCountThreads, sizeof(CountSmem), st>>>(
-                    ts2, cat->n_pairs_padded, nullptr, nullptr, nk, cat->d_off, cat->d_block_row, cat->n_rows,
-                    ws->d_counts, sq);
-                TVZ_CUDA(cudaGetLastError());
+                rc = launch(true, nullptr, nullptr, nk, sq);
+                if (rc) return rc;
             }
         } else {
-            TVZ_CUDA(cudaFuncSetAttribute(match_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(sizeof(CountSmem))));
             for (int k0 = 0; k0 < nk; k0 += kMaxKeys) {
                 const int n = std::min(kMaxKeys, nk - k0);
                 TVZ_CUDA(cudaMemcpyAsync(ws->d_keys, h_keys + k0, sizeof(unsigned long long) * n,
                                          cudaMemcpyHostToDevice, st));
                 TVZ_CUDA(cudaMemcpyAsync(ws->d_mult, h_mult + k0, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-                match_count_kernel<false><<<grid, kCountThreads, sizeof(CountSmem), st>>>(
-                    ts2, cat->n_pairs_padded, ws->d_keys, ws->d_mult, n, cat->d_off, cat->d_block_row, cat->n_rows,
-                    ws->d_counts, SmallQuery{});
-                TVZ_CUDA(cudaGetLastError());
+                rc = launch(false, ws->d_keys, ws->d_mult, n, SmallQuery{});
+                if (rc) return rc;
             }
         }
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
