@@ -131,6 +131,37 @@ const int32_t *tvz_match_ws_hits(const tvz_match_ws *ws);
 const int64_t *tvz_match_ws_nhits(const tvz_match_ws *ws);
 const int32_t *tvz_match_ws_counts(const tvz_match_ws *ws);  /* int32 [rows] scratch (zero between calls) */
 
+/* ------------------------------------------------------------------ fragment mode
+ * Offset-invariant matching of a clip's cut list against longer stored videos
+ * (BASELINE.json config 5).  The reference advertises this (README.md:5) but
+ * implements only offset-0 exact membership (inspector/db.py:78-79), so the
+ * semantics are this library's own (tvidz_b200/csrc/fragment.cu header):
+ *   ticks = llround(ts * tick_hz); candidate offsets d = C[j] - Q[i] come from
+ *   adjacent cut pairs whose intervals agree within tol_gap ticks;
+ *   score(d) = #{i : some C[j] within tol ticks of Q[i] + d}; a row reports its
+ *   best (score, d) -- ties: smaller |d|, then smaller d -- iff score >= min_match.
+ *   zero_offset_only = 1 scores d = 0 alone; with tol 0 that is find_duplicates'
+ *   match_count (db.py:85-89) on tick-exact data.
+ * Calls on one tvz_fragcat are serialised internally.
+ */
+typedef struct tvz_fragcat tvz_fragcat;
+int tvz_fragcat_create(const double *h_ts, const int64_t *h_off, const int32_t *h_video_id, int64_t n_rows,
+                       double tick_hz, int64_t hit_capacity, tvz_fragcat **out);
+void tvz_fragcat_destroy(tvz_fragcat *cat);
+int64_t tvz_fragcat_rows(const tvz_fragcat *cat);
+int64_t tvz_fragcat_values(const tvz_fragcat *cat);   /* stored ticks (4 bytes each) */
+
+/* Host-buffer call: results (catalogue order) in host arrays of `cap` entries. */
+int tvz_fragcat_match(tvz_fragcat *cat, const double *q, int qn, int min_match, int tol_ticks, int tol_gap_ticks,
+                      int zero_offset_only, int32_t *out_video_id, int32_t *out_score, int32_t *out_delta_ticks,
+                      int64_t cap, int64_t *n_out);
+
+/* Device-resident variant: d_out is int32 [3 * (out_cap + 1)] on the device:
+ *   d_out[0..1] = { n_hits saturated, overflow flag }, d_out[2 + 2h ..] = { video_id, score },
+ *   d_out[2 * (out_cap + 1) + 1 + h] = offset ticks of hit h.  One fixed-size record per shard. */
+int tvz_fragcat_match_async(tvz_fragcat *cat, const double *h_q, int qn, int min_match, int tol_ticks,
+                            int tol_gap_ticks, int zero_offset_only, int32_t *d_out, int64_t out_cap, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,9 @@ def lib() -> ctypes.CDLL:
         L.tvzo_match_kth.restype = None
         L.tvzo_match_kth.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_void_p, c.c_int, c.c_int,
                                      c.c_void_p, c.c_int]
+        L.tvzo_fragment_rows.restype = None
+        L.tvzo_fragment_rows.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_void_p, c.c_int, c.c_double, c.c_int,
+                                         c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_int]
         _lib = L
     return _lib
 
@@ -172,3 +175,26 @@ def find_duplicates_csr(ts, off, video_id, q, min_match=5, n_threads: int = 0):
     keep = np.nonzero(counts >= min_match)[0]
     vid = np.asarray(video_id)
     return [(int(vid[r]), int(counts[r])) for r in keep]
+
+
+# ---------------------------------------------------------------- fragment mode (builder-defined spec)
+def fragment_rows(ts, off, q, tick_hz: float = 1000.0, tol: int = 7, tol_gap: int = 14, zero_only: bool = False,
+                  n_threads: int = 0):
+    """Best (score, offset ticks) per row under the interval-anchored spec -> (int32 [N], int64 [N])."""
+    ts = np.ascontiguousarray(ts, np.float64)
+    off = np.ascontiguousarray(off, np.int64)
+    q = np.ascontiguousarray(q, np.float64)
+    n = off.shape[0] - 1
+    score = np.zeros(n, np.int32)
+    delta = np.zeros(n, np.int64)
+    lib().tvzo_fragment_rows(_p(ts), _p(off), n, _p(q), q.shape[0], tick_hz, tol, tol_gap, int(zero_only),
+                             _p(score), _p(delta), n_threads)
+    return score, delta
+
+
+def find_fragments_csr(ts, off, video_id, q, min_match=5, **kw):
+    """[(video_id, score, offset_ticks)] for rows whose best score >= min_match, catalogue order."""
+    score, delta = fragment_rows(ts, off, q, **kw)
+    keep = np.nonzero(score >= min_match)[0]
+    vid = np.asarray(video_id)
+    return [(int(vid[r]), int(score[r]), int(delta[r])) for r in keep]

@@ -1,0 +1,121 @@
+"""Fragment mode on the GPU against this repo's own oracle (parity unpinned: the reference has no
+fragment matcher), plus the one reference-anchored property: at offset 0 with zero tolerance the
+score is find_duplicates' match_count."""
+import numpy as np
+import pytest
+
+import oracle
+from tvidz_b200 import synth
+from tvidz_b200.catalog import Catalogue
+from tvidz_b200.fragment import FragmentCatalogue, clip_query
+
+pytestmark = pytest.mark.gpu
+
+
+def _long_catalogue(n_rows, seed):
+    return synth.synth_catalogue(n_rows, len_range=(600, 1400), gap_range=(15, 150), seed=seed)
+
+
+def test_clip_is_found_at_its_offset(cuda):
+    ts, off, vid = _long_catalogue(400, seed=11)
+    cat = FragmentCatalogue(ts, off, vid)
+    rng = np.random.default_rng(11)
+    for _ in range(6):
+        r = int(rng.integers(400))
+        row = ts[off[r]:off[r + 1]]
+        f0 = int(rng.integers(0, int(row[-1] * 30) - 900))
+        q = clip_query(row, f0)
+        if len(q) < 5:
+            continue
+        got = cat.find_fragments(q, min_match=len(q))
+        want = oracle.find_fragments_csr(ts, off, vid, q, min_match=len(q))
+        assert [(v, s) for v, s, _ in got] == [(v, s) for v, s, _ in want]
+        hit = [g for g in got if g[0] == int(vid[r])]
+        assert hit and hit[0][1] == len(q) and abs(hit[0][2] - f0 / 30.0) <= 0.008
+    cat.close()
+
+
+@pytest.mark.parametrize("min_match", [2, 3, 5])
+def test_matches_oracle_all_rows(cuda, min_match):
+    ts, off, vid = _long_catalogue(1500, seed=5)
+    cat = FragmentCatalogue(ts, off, vid, hit_capacity=8)          # forces the capacity regrowth path
+    row = ts[off[77]:off[78]]
+    q = clip_query(row, 12_345)
+    v, s, d = cat.match(q, min_match)
+    want = oracle.find_fragments_csr(ts, off, vid, q, min_match=min_match)
+    assert list(zip(v.tolist(), s.tolist(), d.tolist())) == want
+    assert len(want) > 1 or min_match == 5
+    cat.close()
+
+
+def test_short_rows_tolerances_and_edges(cuda):
+    rows = [(1, [0.5, 1.0, 2.5, 4.0]), (2, [100.5, 101.0, 102.5, 104.0, 250.0]), (3, []), (4, [7.0]),
+            (5, [10.0, 10.5]), (6, [4.0, 2.5, 1.0, 0.5, 0.5, float("nan")]),        # unsorted, repeat, NaN
+            (7, [1000.503, 1001.004, 1002.498, 1003.999])]                            # 3-4 ms off
+    from tvidz_b200.catalog import rows_to_csr
+    ts, off, vid = rows_to_csr(rows)
+    cat = FragmentCatalogue(ts, off, vid)
+    q = [0.5, 1.0, 2.5, 4.0]
+    for tol, tol_gap in ((0, 0), (2, 4), (7, 14)):
+        for mm in (0, 1, 2, 4):
+            v, s, d = cat.match(q, mm, tol=tol, tol_gap=tol_gap)
+            assert list(zip(v.tolist(), s.tolist(), d.tolist())) == \
+                oracle.find_fragments_csr(ts, off, vid, q, min_match=mm, tol=tol, tol_gap=tol_gap), (tol, mm)
+    res = dict((v, (s, o)) for v, s, o in cat.find_fragments(q, 4))
+    assert res[1] == (4, 0.0) and res[2] == (4, 100.0) and res[6] == (4, 0.0) and res[7][0] == 4
+    assert 7 not in dict((v, s) for v, s, _ in cat.find_fragments(q, 4, tol=0, tol_gap=0))
+    assert cat.find_fragments([], 1) == [] and cat.find_fragments([3.0], 1) == []      # no interval, no anchor
+    assert cat.find_fragments(q, 4, top_k=2)[0][1] == 4
+    cat.close()
+
+
+def test_zero_offset_collapses_to_find_duplicates(cuda):
+    """offset 0, tolerance 0 == match_count of db.py:85-89 on tick-exact data."""
+    rng = np.random.default_rng(3)
+    rows = [(i + 1, np.unique(rng.integers(0, 4000, int(rng.integers(0, 60))) / 8.0).tolist()) for i in range(800)]
+    from tvidz_b200.catalog import rows_to_csr
+    ts, off, vid = rows_to_csr(rows)
+    frag = FragmentCatalogue(ts, off, vid)
+    exact = Catalogue(ts, off, vid)
+    for _ in range(5):
+        q = np.unique(rng.integers(0, 4000, 40) / 8.0)
+        for mm in (1, 2, 4):
+            v, s, d = frag.match(q, mm, tol=0, tol_gap=0, zero_offset_only=True)
+            assert list(zip(v.tolist(), s.tolist())) == exact.find_duplicates(q, mm) == \
+                oracle.find_duplicates_csr(ts, off, vid, q, mm)
+            assert not d.any()
+    frag.close()
+    exact.close()
+
+
+def test_long_rows_read_in_place(cuda):
+    """Rows longer than the 2048-tick shared-memory buffer take the in-place path."""
+    ts, off, vid = synth.synth_catalogue(12, len_range=(2500, 5000), gap_range=(15, 150), seed=2)
+    cat = FragmentCatalogue(ts, off, vid)
+    row = ts[off[5]:off[6]]
+    q = clip_query(row, 30_000, n_frames=1800)
+    v, s, d = cat.match(q, 3)
+    assert list(zip(v.tolist(), s.tolist(), d.tolist())) == oracle.find_fragments_csr(ts, off, vid, q, min_match=3)
+    assert (int(vid[5]), len(q)) in list(zip(v.tolist(), s.tolist()))
+    cat.close()
+
+
+def test_full_size_config5(cuda):
+    """BASELINE config 5 geometry: a 30 s clip against 100k long videos.  Oracle on a 3000-row
+    slice around the source row; size-independent property on the whole catalogue (the source row
+    is reported with every cut and the right offset)."""
+    ts, off, vid = _long_catalogue(100_000, seed=0)
+    cat = FragmentCatalogue(ts, off, vid)
+    r = 54_321
+    row = ts[off[r]:off[r + 1]]
+    f0 = 40_000
+    q = clip_query(row, f0)
+    assert len(q) >= 6
+    got = cat.find_fragments(q, min_match=5)
+    top = cat.find_fragments(q, min_match=5, top_k=1)[0]
+    assert top[0] == int(vid[r]) and top[1] == len(q) and abs(top[2] - f0 / 30.0) <= 0.008
+    lo, hi = r - 1500, r + 1500
+    sub = oracle.find_fragments_csr(ts[off[lo]:off[hi]], off[lo:hi + 1] - off[lo], vid[lo:hi], q, min_match=5)
+    ids = set(vid[lo:hi].tolist())
+    assert [(v, s, round(o * 1000)) for v, s, o in got if v in ids] == sub
+    cat.close()

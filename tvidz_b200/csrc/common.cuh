@@ -15,6 +15,12 @@ char *err_buf();                       // thread-local, 512 bytes
 int set_error(int code, const char *fmt, ...);
 int num_sms();                          // SM count of the current device (cached per device)
 
+// match.cu: single-pass ordered compaction shared by find_duplicates and fragment mode
+int compact_blocks(long long n_rows);
+int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid, int *out, long long *rows_out,
+                    long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket,
+                    const int *aux, int *aux_out, cudaStream_t st);
+
 #define TVZ_CUDA(expr)                                                                        \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \

@@ -195,7 +195,8 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
 __global__ void __launch_bounds__(kScanThreads)
 match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, const int *__restrict__ vid,
                      int *__restrict__ out, long long *__restrict__ rows_out, long long cap,
-                     long long *__restrict__ n_hits_out, unsigned long long *state, unsigned *ticket) {
+                     long long *__restrict__ n_hits_out, unsigned long long *state, unsigned *ticket,
+                     const int *__restrict__ aux, int *__restrict__ aux_out) {
     // ticket[0] = next ticket, ticket[1] = query epoch.  The epoch is read BEFORE the ticket is
     // taken and bumped by the holder of the last ticket, i.e. after every block has read it:
     // the kernel is self-contained and can be replayed from a CUDA graph.
@@ -296,6 +297,7 @@ match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, 
                 out[2 + 2 * pos] = vid[r0 + j];
                 out[3 + 2 * pos] = cnt[j];
                 rows_out[pos] = r0 + j;
+                if (aux) aux_out[1 + pos] = aux[r0 + j];  // per-row payload (fragment mode: best offset)
             }
             ++pos;
         }
@@ -332,6 +334,22 @@ __global__ void match_kth_kernel(const unsigned long long *__restrict__ ts, cons
 }
 
 }  // namespace
+
+int compact_blocks(long long n_rows) {
+    return static_cast<int>((n_rows + kScanRowsPerBlock - 1) / kScanRowsPerBlock);
+}
+
+// Ordered compaction of counts[row] >= min_match (see match_compact_kernel).  `state` holds
+// compact_blocks(n_rows) u64 records (zero-initialised once), `ticket` two u32 {0, 1}.
+int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid, int *out, long long *rows_out,
+                    long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket,
+                    const int *aux, int *aux_out, cudaStream_t st) {
+    match_compact_kernel<<<compact_blocks(n_rows), kScanThreads, 0, st>>>(counts, n_rows, min_match, vid, out, rows_out,
+                                                                          cap, n_hits_out, state, ticket, aux, aux_out);
+    TVZ_CUDA(cudaGetLastError());
+    return TVZ_OK;
+}
+
 }  // namespace tvz
 
 using namespace tvz;
@@ -647,10 +665,9 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
             }
         }
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
-        match_compact_kernel<<<ws->n_blocks, kScanThreads, 0, st>>>(ws->d_counts, cat->n_rows, min_match, cat->d_vid,
-                                                                    d_out, ws->d_rows, out_cap, ws->d_nhits,
-                                                                    ws->d_state, ws->d_ticket);
-        TVZ_CUDA(cudaGetLastError());
+        rc = compact_enqueue(ws->d_counts, cat->n_rows, min_match, cat->d_vid, d_out, ws->d_rows, out_cap, ws->d_nhits,
+                             ws->d_state, ws->d_ticket, nullptr, nullptr, st);
+        if (rc) return rc;
         if (want_kth) {
             match_kth_kernel<<<2 * sms, 256, 0, st>>>(cat->d_ts, cat->d_off, ws->d_rows, d_out, out_cap,
                                                       ws->d_qcanon, qn, min_match, ws->d_kth);

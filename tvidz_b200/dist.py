@@ -98,3 +98,50 @@ class ShardedCatalogue:
             if not overflow:
                 return list(zip(pairs[:, 0].tolist(), pairs[:, 1].tolist()))
             self._alloc(max(needed, 2 * self.cap))     # every rank sees the same records -> same decision
+
+
+class ShardedFragmentCatalogue:
+    """Fragment matching over a row-sharded catalogue: per-shard fixed-size records
+    (int32 [3 * (cap + 1)]) gathered with one all-gather, merged in catalogue order, top-k on the host."""
+
+    def __init__(self, ts, off, video_id, tick_hz: float = 1000.0, hit_capacity: int = 1 << 12, device=None,
+                 local_factory: Callable | None = None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.tick_hz = float(tick_hz)
+        self.bounds = shard_bounds(off, self.world)
+        lo, hi = self.bounds[self.rank]
+        s_ts, s_off, s_vid = take_shard(np.asarray(ts), np.asarray(off), np.asarray(video_id), lo, hi)
+        if local_factory is None:
+            from .fragment import FragmentCatalogue
+            dev = torch.cuda.current_device() if device is None else device
+            self.device = torch.device("cuda", dev)
+            self.local = FragmentCatalogue(s_ts, s_off, s_vid, tick_hz=tick_hz, device=dev, hit_capacity=hit_capacity)
+        else:
+            self.device = torch.device("cpu") if device is None else torch.device(device)
+            self.local = local_factory(s_ts, s_off, s_vid)
+        self._alloc(hit_capacity)
+
+    def _alloc(self, cap: int) -> None:
+        self.cap = int(cap)
+        self.record = torch.zeros(3 * (self.cap + 1), dtype=torch.int32, device=self.device)
+        self.gathered = torch.zeros(self.world * 3 * (self.cap + 1), dtype=torch.int32, device=self.device)
+
+    def enqueue(self, clip_timestamps, min_match: int, **kw) -> None:
+        self.local.match_async(clip_timestamps, min_match, self.record, **kw)
+        dist.all_gather_into_tensor(self.gathered, self.record, group=self.group)
+
+    def find_fragments(self, clip_timestamps, min_match: int = 5, top_k: int | None = None, **kw):
+        from .fragment import rank_fragments
+        while True:
+            self.enqueue(clip_timestamps, min_match, **kw)
+            g = self.gathered.view(self.world, 3 * (self.cap + 1)).cpu().numpy()
+            pairs, overflow, needed = merge_records(g[:, : 2 * (self.cap + 1)].reshape(self.world, self.cap + 1, 2),
+                                                    self.cap)
+            if overflow:
+                self._alloc(max(needed, 2 * self.cap))
+                continue
+            deltas = [g[r, 2 * (self.cap + 1) + 1: 2 * (self.cap + 1) + 1 + int(g[r, 0])] for r in range(self.world)]
+            delta = np.concatenate(deltas) if deltas else np.zeros(0, np.int32)
+            return rank_fragments(pairs[:, 0], pairs[:, 1], delta, self.tick_hz, top_k)
