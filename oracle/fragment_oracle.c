@@ -29,7 +29,7 @@ static int canon_ticks(const double *ts, int64_t n, double hz, int64_t *out)
     int m = 0;
     for (int64_t i = 0; i < n; i++) {
         double v = ts[i] * hz;
-        if (!isfinite(v) || fabs(v) > 2.0e9) continue;
+        if (!isfinite(v) || fabs(v) > 5.0e8) continue;
         out[m++] = llround(v);
     }
     qsort(out, (size_t)m, sizeof(int64_t), cmp_i64);

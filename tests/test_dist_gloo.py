@@ -33,6 +33,26 @@ class OracleShard:
         out[1:1 + n, 1] = torch.from_numpy(counts[keep[:n]].astype(np.int32))
 
 
+class OracleFragmentShard:
+    """CPU stand-in for FragmentCatalogue.match_async, same int32 [3 * (cap + 1)] record."""
+
+    def __init__(self, ts, off, vid):
+        self.ts, self.off, self.vid = ts, off, vid
+
+    def match_async(self, q, min_match, out, **kw):
+        score, delta = oracle.fragment_rows(self.ts, self.off, np.asarray(q, np.float64), **kw)
+        keep = np.nonzero(score >= min_match)[0]
+        cap = out.numel() // 3 - 1
+        out.zero_()
+        out[0] = min(len(keep), 2**31 - 1)
+        out[1] = int(len(keep) > cap)
+        n = min(len(keep), cap)
+        rec = out[2:2 + 2 * n].view(n, 2)
+        rec[:, 0] = torch.from_numpy(self.vid[keep[:n]].astype(np.int32))
+        rec[:, 1] = torch.from_numpy(score[keep[:n]].astype(np.int32))
+        out[2 * (cap + 1) + 1: 2 * (cap + 1) + 1 + n] = torch.from_numpy(delta[keep[:n]].astype(np.int32))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -55,6 +75,19 @@ def _worker(rank, world, port, q_out):
             want = oracle.find_duplicates_csr(ts, off, vid, q, mm)
             results.append(got == want)
         results.append(sc.cap >= 5000 // world)           # grew past the tiny initial capacity
+        # fragment mode through the same gather: 30 s clip out of row 123 of a long-row catalogue
+        from tvidz_b200.dist import ShardedFragmentCatalogue
+        from tvidz_b200.fragment import clip_query, rank_fragments
+        fts, foff, fvid = synth.synth_catalogue(240, len_range=(300, 700), gap_range=(15, 150), seed=5)
+        fq = clip_query(fts[foff[123]:foff[124]], 9000)
+        fc = ShardedFragmentCatalogue(fts, foff, fvid, hit_capacity=4, local_factory=OracleFragmentShard)
+        for mm, k in ((3, None), (len(fq), 1), (2, 5)):
+            got = fc.find_fragments(fq, mm, top_k=k)
+            sc_, dl_ = oracle.fragment_rows(fts, foff, np.asarray(fq))
+            keep = np.nonzero(sc_ >= mm)[0]
+            want = rank_fragments(fvid[keep], sc_[keep], dl_[keep], 1000.0, k)
+            results.append(got == want and len(got) >= 1)
+        results.append(fc.find_fragments(fq, len(fq), top_k=1)[0][0] == int(fvid[123]))
         q_out.put((rank, results, sc.bounds))
     except Exception as e:  # surface the failure instead of letting the parent time out
         q_out.put((rank, [False, repr(e)], []))
