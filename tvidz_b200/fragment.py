@@ -1,8 +1,8 @@
 """Fragment (offset-invariant) matching: a clip's cut list against longer stored videos
 (BASELINE.json config 5).  The reference only advertises this (README.md:5); its matcher is
 offset-0 exact membership (inspector/db.py:78-79).  The semantics are therefore this
-package's own -- "interval-anchored alignment", stated in csrc/fragment.cu and restated by
-oracle/fragment_oracle.c (parity unpinned) -- and collapse to find_duplicates' match_count at
+package's own -- "interval-anchored alignment", stated in csrc/fragment.cu and restated by the
+repo's CPU checker (test infrastructure; parity unpinned) -- and collapse to find_duplicates' match_count at
 offset 0 with zero tolerance on tick-exact data.
 """
 from __future__ import annotations
