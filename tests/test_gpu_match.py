@@ -177,3 +177,45 @@ def test_full_size_million_rows(cuda):
     assert set(got5) <= set(got2) and len(got2) > len(got5) >= 1
     assert cat.find_duplicates(q, len(q)) == [(int(vid[r]), len(q))]
     cat.close()
+
+
+def test_reference_style_per_cut_loop_uses_the_overlay(cuda, stream_golden):
+    """The unmodified shape of app.py:228-255 -- add_timestamps() then find_duplicates() after every
+    new cut -- against a 30k-row catalogue: same verdicts as the oracle's streaming loop, and the big
+    catalogue is packed exactly once (row rewrites go to the overlay + tombstones)."""
+    ts, off, vid = synth.synth_catalogue(30_000, seed=12)
+    ins = Inspector()
+    rows = []
+    for r in range(30_000):
+        row = ts[off[r]:off[r + 1]].tolist()
+        ins._rows[r + 1] = row
+        rows.append((r + 1, row))
+    ins._next_id = 30_001
+    assert ins.find_duplicates([1.0], 1) is not None and ins.repacks == 1
+    for src in (10, 20_000, 29_999):
+        me = ins.add_video("upload-%d.mp4" % src)
+        tokens = ["%.6g" % t for t in rows[src][1]]
+        scene, dups = [], []
+        for tok in tokens:                                   # app.py:228-255, verbatim shape
+            t = float(tok)
+            if not scene or t != scene[-1]:
+                scene.append(t)
+                ins.add_timestamps(me.id, scene)
+                dups = [d for d in ins.find_duplicates(scene, min_match=2) if d[0] != me.id]
+                if dups:
+                    break
+        o_scene, o_ids, _ = match_oracle.streaming_analysis(rows, me.id, tokens, 2)
+        assert scene == o_scene and [d[0] for d in dups] == o_ids and src + 1 in o_ids
+        rows.append((me.id, list(scene)))                    # the truncated row stays in the catalogue (Q5)
+    # rewriting a packed row hides its old content and serves the new one
+    ins.add_timestamps(11, [123456.5, 123457.5])
+    assert ins.find_duplicates(rows[10][1], 5) == [d for d in
+                                                   match_oracle.find_duplicates(rows, rows[10][1], 5) if d[0] != 11]
+    assert (11, 2) in ins.find_duplicates([123456.5, 123457.5], 2)
+    assert ins.repacks == 1
+    small = Inspector(overlay_limit=2)                      # the overlay folds into a fresh pack when it outgrows its limit
+    for i in range(6):
+        v = small.add_video("v%d" % i)
+        small.add_timestamps(v.id, [float(i), float(i) + 0.5])
+        assert small.find_duplicates([float(i), float(i) + 0.5], 2) == [(v.id, 2)]
+    assert small.repacks == 2 and small.find_duplicates([0.0, 0.5, 3.0, 3.5], 2) == [(1, 2), (4, 2)]

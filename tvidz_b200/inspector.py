@@ -29,14 +29,30 @@ class Video:                                   # db.py:12-20
 
 
 class Inspector:
-    def __init__(self, device: int | None = None):
+    """Videos + `video_timestamps` rows in process memory, matched on the GPU.
+
+    The packed device catalogue is immutable; row updates go to a small overlay catalogue and
+    a tombstone set so that the reference's per-cut pattern -- add_timestamps() then
+    find_duplicates() for every new cut (app.py:234-235) -- never repacks the big catalogue.
+    The overlay is folded into a fresh pack once it outgrows `overlay_limit` rows.
+    Result order: rows in order of their last write (the reference's own order is Postgres heap
+    order, db.py:83, which also moves a row on UPDATE).
+    """
+
+    def __init__(self, device: int | None = None, overlay_limit: int | None = None):
         self._device = device
         self._lock = threading.RLock()
         self._videos: dict[int, Video] = {}
-        self._rows: dict[int, list[float]] = {}     # video_id -> timestamps (insertion order = row order)
+        self._rows: dict[int, list[float]] = {}     # video_id -> timestamps, ordered by last write
         self._next_id = 1
-        self._catalogue: Catalogue | None = None
-        self._dirty = True
+        self._overlay_limit = overlay_limit
+        self._main: Catalogue | None = None         # packed snapshot
+        self._main_ids: set[int] = set()
+        self._tomb: set[int] = set()                # ids in the snapshot whose row was rewritten since
+        self._overlay_rows: dict[int, list[float]] = {}
+        self._overlay: Catalogue | None = None
+        self._overlay_dirty = False
+        self.repacks = 0                            # observability: full packs of the big catalogue
 
     # ---------------------------------------------------------------- db.py mirror
     def add_video(self, filename, thumbnail_path=None) -> Video:          # db.py:32-41
@@ -47,9 +63,16 @@ class Inspector:
             return v
 
     def add_timestamps(self, video_id, timestamps) -> None:               # db.py:43-64 (upsert)
+        row = [float(x) for x in timestamps]
         with self._lock:
-            self._rows[video_id] = [float(x) for x in timestamps]
-            self._dirty = True
+            self._rows.pop(video_id, None)
+            self._rows[video_id] = row                                    # last write goes last
+            if self._main is not None:
+                if video_id in self._main_ids:
+                    self._tomb.add(video_id)
+                self._overlay_rows.pop(video_id, None)
+                self._overlay_rows[video_id] = row
+                self._overlay_dirty = True
 
     def update_duplicates(self, video_id, duplicate_ids) -> None:         # db.py:66-74
         with self._lock:
@@ -72,21 +95,53 @@ class Inspector:
             self._videos.clear()
             self._rows.clear()
             self._next_id = 1
-            self._dirty = True
+            self._drop_packs()
 
-    def _packed(self) -> Catalogue:
+    def _drop_packs(self) -> None:
+        for c in (self._main, self._overlay):
+            if c is not None:
+                c.close()
+        self._main = self._overlay = None
+        self._main_ids, self._tomb, self._overlay_rows = set(), set(), {}
+        self._overlay_dirty = False
+
+    def _packs(self):
+        """-> (main catalogue, tombstoned ids as int32 array, overlay catalogue or None)."""
         with self._lock:
-            if self._dirty or self._catalogue is None:
-                if self._catalogue is not None:
-                    self._catalogue.close()
-                self._catalogue = Catalogue(*rows_to_csr(self._rows.items()), device=self._device)
-                self._dirty = False
-            return self._catalogue
+            limit = self._overlay_limit if self._overlay_limit is not None else max(1024, len(self._main_ids) // 64)
+            if self._main is None or len(self._overlay_rows) > limit:
+                self._drop_packs()
+                self._main = Catalogue(*rows_to_csr(self._rows.items()), device=self._device)
+                self._main_ids = set(self._rows.keys())
+                self.repacks += 1
+            if self._overlay_dirty:
+                if self._overlay is not None:
+                    self._overlay.close()
+                self._overlay = Catalogue(*rows_to_csr(self._overlay_rows.items()), device=self._device,
+                                          hit_capacity=4096)
+                self._overlay_dirty = False
+            tomb = np.fromiter(self._tomb, np.int32, len(self._tomb))
+            return self._main, tomb, self._overlay
+
+    def _match(self, new_timestamps, min_match: int, with_kth: bool = False):
+        with self._lock:        # a concurrent upsert may retire the packs: queries on one Inspector serialise
+            return self._match_locked(new_timestamps, min_match, with_kth)
+
+    def _match_locked(self, new_timestamps, min_match: int, with_kth: bool):
+        main, tomb, overlay = self._packs()
+        parts = [main.match(new_timestamps, min_match, with_kth)]
+        if tomb.size:
+            keep = ~np.isin(parts[0][0], tomb)
+            parts[0] = tuple(a[keep] for a in parts[0])
+        if overlay is not None:
+            parts.append(overlay.match(new_timestamps, min_match, with_kth))
+        return tuple(np.concatenate(cols) for cols in zip(*parts))
 
     def find_duplicates(self, new_timestamps, min_match=5):               # db.py:76-94
         """[(video_id, match_count)] for every stored row with at least `min_match` of the
-        query's timestamps (exact equality, self included), in row order."""
-        return self._packed().find_duplicates(new_timestamps, min_match)
+        query's timestamps (exact equality, self included)."""
+        vid, cnt = self._match(new_timestamps, min_match)
+        return list(zip(vid.tolist(), cnt.tolist()))
 
     # ---------------------------------------------------------------- app.py:216-302
     def analyze_cuts(self, video_id: int, pts_time_tokens: Iterable, min_match: int = 2):
@@ -105,7 +160,7 @@ class Inspector:
             raise ValueError("the streaming loop needs min_match >= 1")
         if not cuts:
             return cuts, []
-        vid, cnt, kth = self._packed().match(cuts, min_match, with_kth=True)
+        vid, cnt, kth = self._match(cuts, min_match, with_kth=True)
         keep = vid != video_id                                # app.py:237 drops self
         vid, kth = vid[keep], kth[keep]
         if vid.size == 0:
