@@ -36,6 +36,17 @@ CATALOGUE_ROWS = 1_000_000
 PYTHON_MATCH_SAMPLE_ROWS = 100_000
 
 
+def ncu_traffic(kernel: str):
+    """dram read+write bytes per launch of `kernel` from the committed ncu --set full capture
+    (profiles/traffic.json, written from the .ncu-rep by scripts/ncu_summary.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(kernel)
+    except OSError:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -208,6 +219,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # Libraries (NCCL prints its version banner) may write to stdout: park fd 1 on stderr so that the
+    # JSON line is the only thing rank 0 ever prints there.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: tvidz_b200 has no CPU path")
     torch.cuda.set_device(local)
@@ -303,7 +319,7 @@ def run_ours(args):
         r_star = 123_456
         q = ts[off[r_star]:off[r_star + 1]].copy()
         mm = 2
-        cap = 1 << 16
+        cap = max(4096, (1 << 15) // world)      # per-shard hit record; regrown on overflow
         if world == 1:
             cat = Catalogue(ts, off, vid, device=local, hit_capacity=cap)
             record = torch.zeros((cap + 1, 2), dtype=torch.int32, device=dev)
@@ -361,7 +377,8 @@ def run_ours(args):
                             "path": "Catalogue.find_duplicates: host query in, Python list of tuples out"},
                     "roofline": {"bound": "hbm", "achieved": local_algo / (count_ms * 1e-3) / 1e9,
                                  "peak": peak_gbs, "unit": "GB/s",
-                                 "frac": local_algo / (count_ms * 1e-3) / 1e9 / peak_gbs, "traffic": None,
+                                 "frac": local_algo / (count_ms * 1e-3) / 1e9 / peak_gbs,
+                                 "traffic": ncu_traffic("match_count_kernel") if world == 1 else None,
                                  "kernel": "match_count_kernel", "kernel_ms": count_ms,
                                  "algorithmic_bytes_per_launch": int(local_algo),
                                  "note": "per GPU (slowest rank); algorithmic bytes 8*values + 8*(rows+1) of "
@@ -446,7 +463,7 @@ def run_ours(args):
                            "cuts_found": n_cuts},
                 "e2e": e2e, "gpu_launches": 2 * K,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                             "frac": achieved / peak_gbs, "traffic": None,
+                             "frac": achieved / peak_gbs, "traffic": ncu_traffic("sad_bulk_kernel"),
                              "kernel": "sad_bulk_kernel (TMA bulk ring, read-once)", "kernel_ms": sad_ms,
                              "algorithmic_bytes_per_launch": int(algo_bytes),
                              "note": "W*H bytes per scored frame (SURVEY.md 8d) x streams x (frames-1)",
@@ -458,7 +475,10 @@ def run_ours(args):
             line["matching"] = matching
         if fragment is not None:
             line["fragment"] = fragment
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
     return 0

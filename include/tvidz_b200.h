@@ -127,6 +127,20 @@ int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q,
  */
 int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn,
                             int min_match, int32_t *d_out, int64_t out_cap, void *stream);
+/* Sharded matcher with the gather fused into the kernel (one process per GPU, peers reachable
+ * over NVLink): like tvz_catalog_match_async into the workspace's own record, but the
+ * compaction's last block then STORES this rank's record ({n_hits, overflow} + hits) into
+ * every peer's gather buffer and raises a per-rank flag there with a system-scope release;
+ * a one-warp kernel enqueued behind it waits until the flags of all peers show `epoch`.
+ *   peer_record[p] : device address (peer memory) of THIS rank's slot, int32 [out_cap + 1][2],
+ *                    inside peer p's gather buffer; peer_flag[p]: this rank's uint32 flag on peer p
+ *   d_my_flags     : this rank's own flag array, uint32 [n_peers] (written by the peers)
+ * Use a different buffer set for consecutive epochs (double buffering): a peer may start
+ * query k+1 while this rank still reads the records of query k.  n_peers <= 8. */
+int tvz_catalog_match_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn,
+                                   int min_match, int n_peers, const uint64_t *peer_record,
+                                   const uint64_t *peer_flag, const uint32_t *d_my_flags, int64_t out_cap,
+                                   uint32_t epoch, void *stream);
 const int32_t *tvz_match_ws_hits(const tvz_match_ws *ws);
 const int64_t *tvz_match_ws_nhits(const tvz_match_ws *ws);
 const int32_t *tvz_match_ws_counts(const tvz_match_ws *ws);  /* int32 [rows] scratch (zero between calls) */

@@ -123,6 +123,21 @@ class Catalogue:
             check(lib().tvz_catalog_match_async(self._handle, ws, q.ctypes.data, q.shape[0], int(min_match),
                                                 out.data_ptr(), cap, int(st.cuda_stream)))
 
+    def match_gather_async(self, new_timestamps, min_match: int, peer_record: np.ndarray, peer_flag: np.ndarray,
+                           my_flags_ptr: int, out_cap: int, epoch: int, stream=None) -> None:
+        """Enqueue one query whose per-shard record is stored straight into every peer's gather
+        buffer by the compaction kernel (tvz_catalog_match_gather_async)."""
+        q = np.ascontiguousarray(np.asarray(new_timestamps, dtype=np.float64).reshape(-1))
+        peer_record = np.ascontiguousarray(peer_record, np.uint64)
+        peer_flag = np.ascontiguousarray(peer_flag, np.uint64)
+        ws = self._ws(out_cap)
+        st = torch.cuda.current_stream(self.device) if stream is None else stream
+        with torch.cuda.device(self.device):
+            check(lib().tvz_catalog_match_gather_async(self._handle, ws, q.ctypes.data, q.shape[0], int(min_match),
+                                                       int(peer_record.shape[0]), peer_record.ctypes.data,
+                                                       peer_flag.ctypes.data, int(my_flags_ptr), int(out_cap),
+                                                       int(epoch) & 0xffffffff, int(st.cuda_stream)))
+
     def debug_count_kernel_ms(self, enable: bool | None = None) -> float | None:
         """Bench hook: enable event timing of the count kernel on this thread's workspace, or
         (enable=None) read the duration of the last query's count kernel in ms."""

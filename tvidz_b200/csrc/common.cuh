@@ -15,11 +15,23 @@ char *err_buf();                       // thread-local, 512 bytes
 int set_error(int code, const char *fmt, ...);
 int num_sms();                          // SM count of the current device (cached per device)
 
-// match.cu: single-pass ordered compaction shared by find_duplicates and fragment mode
+// Fused gather (multi-GPU matcher): where the compaction's last block stores this rank's hit
+// record on every peer, and the flag it raises there afterwards.
+constexpr int kMaxPeers = 8;
+struct GatherTargets {
+    int n_peers = 0;                 // 0 = no gather
+    unsigned epoch = 0;
+    int *record[kMaxPeers] = {};     // this rank's slot inside peer p's gather buffer (peer memory)
+    unsigned *flag[kMaxPeers] = {};  // this rank's flag word on peer p
+};
+
+// match.cu: single-pass ordered compaction shared by find_duplicates and fragment mode.
+// `ticket` holds three u32 {next ticket = 0, query epoch = 1, finished blocks = 0}.
 int compact_blocks(long long n_rows);
 int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid, int *out, long long *rows_out,
                     long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket,
-                    const int *aux, int *aux_out, cudaStream_t st);
+                    const int *aux, int *aux_out, cudaStream_t st, const GatherTargets *gather = nullptr);
+int gather_wait_enqueue(const unsigned *d_flags, int n_peers, unsigned epoch, cudaStream_t st);
 
 #define TVZ_CUDA(expr)                                                                        \
     do {                                                                                      \

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kScanThreads)
 match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, const int *__restrict__ vid,
                      int *__restrict__ out, long long *__restrict__ rows_out, long long cap,
                      long long *__restrict__ n_hits_out, unsigned long long *state, unsigned *ticket,
-                     const int *__restrict__ aux, int *__restrict__ aux_out) {
+                     const int *__restrict__ aux, int *__restrict__ aux_out, const __grid_constant__ GatherTargets gt) {
     // ticket[0] = next ticket, ticket[1] = query epoch.  The epoch is read BEFORE the ticket is
     // taken and bumped by the holder of the last ticket, i.e. after every block has read it:
     // the kernel is self-contained and can be replayed from a CUDA graph.
@@ -302,6 +302,45 @@ match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, 
             ++pos;
         }
     }
+    if (gt.n_peers == 0) return;
+
+    // ---- fused gather: the block that finishes last ships this rank's record to every peer ----
+    // (stores over NVLink into peer memory, then a system-scope release of the per-rank flag)
+    __shared__ unsigned s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();  // this block's out[] writes (and the header, if it wrote it) before the count
+        const unsigned done = atomicAdd(ticket + 2, 1u);
+        s_last = done == gridDim.x - 1;
+        if (s_last) ticket[2] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const long long hdr = *reinterpret_cast<volatile int *>(out);      // n_hits (saturated), written before
+    const int words = 2 * (1 + static_cast<int>(min(hdr, cap)));     // the header's block counted itself done
+    for (int p = 0; p < gt.n_peers; ++p) {
+        int *dst = gt.record[p];
+        if (dst == out) continue;  // single-GPU / self slot aliases the local record
+        for (int i = threadIdx.x; i < words; i += kScanThreads) dst[i] = __ldcg(out + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < gt.n_peers)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gt.flag[threadIdx.x]), "r"(gt.epoch) : "memory");
+}
+
+// Wait until every peer's record for `epoch` has landed in this rank's gather buffer.  Bounded:
+// a peer that never answers turns into a launch failure, not a hung GPU.
+__global__ void gather_wait_kernel(const unsigned *flags, int n_peers, unsigned epoch) {
+    if (threadIdx.x >= n_peers) return;
+    unsigned v, polls = 0;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+        if (v == epoch) return;
+        __nanosleep(64);
+    } while (++polls < (1u << 26));
+    __trap();
 }
 
 // Per hit row: the 1-based query index at which the row reaches min_match.
@@ -343,9 +382,17 @@ int compact_blocks(long long n_rows) {
 // compact_blocks(n_rows) u64 records (zero-initialised once), `ticket` two u32 {0, 1}.
 int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid, int *out, long long *rows_out,
                     long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket,
-                    const int *aux, int *aux_out, cudaStream_t st) {
+                    const int *aux, int *aux_out, cudaStream_t st, const GatherTargets *gather) {
+    const GatherTargets none{};
     match_compact_kernel<<<compact_blocks(n_rows), kScanThreads, 0, st>>>(counts, n_rows, min_match, vid, out, rows_out,
-                                                                          cap, n_hits_out, state, ticket, aux, aux_out);
+                                                                          cap, n_hits_out, state, ticket, aux, aux_out,
+                                                                          gather ? *gather : none);
+    TVZ_CUDA(cudaGetLastError());
+    return TVZ_OK;
+}
+
+int gather_wait_enqueue(const unsigned *d_flags, int n_peers, unsigned epoch, cudaStream_t st) {
+    gather_wait_kernel<<<1, 32, 0, st>>>(d_flags, n_peers, epoch);
     TVZ_CUDA(cudaGetLastError());
     return TVZ_OK;
 }
@@ -534,10 +581,10 @@ int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_
     if ((e = cudaMemset(ws->d_counts, 0, nr * 4)) != cudaSuccess) return bail(e, "cudaMemset(counts)");
     if ((e = cudaMalloc(&ws->d_state, std::max(1, ws->n_blocks) * 8)) != cudaSuccess) return bail(e, "cudaMalloc(state)");
     if ((e = cudaMemset(ws->d_state, 0, std::max(1, ws->n_blocks) * 8)) != cudaSuccess) return bail(e, "cudaMemset(state)");
-    if ((e = cudaMalloc(&ws->d_ticket, 8)) != cudaSuccess) return bail(e, "cudaMalloc(ticket)");
+    if ((e = cudaMalloc(&ws->d_ticket, 12)) != cudaSuccess) return bail(e, "cudaMalloc(ticket)");
     {
-        const unsigned init[2] = {0u, 1u};
-        if ((e = cudaMemcpy(ws->d_ticket, init, 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+        const unsigned init[3] = {0u, 1u, 0u};
+        if ((e = cudaMemcpy(ws->d_ticket, init, 12, cudaMemcpyHostToDevice)) != cudaSuccess)
             return bail(e, "cudaMemcpy(ticket)");
     }
     if ((e = cudaMalloc(&ws->d_out, (ws->cap + 1) * 8)) != cudaSuccess) return bail(e, "cudaMalloc(out)");
@@ -599,10 +646,13 @@ namespace {
 
 // Enqueue query upload + count + ordered compaction (+ kth) on `st`.  `want_kth` needs qn <= q_cap.
 int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match, bool want_kth,
-                  int *d_out, long long out_cap, cudaStream_t st) {
+                  int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr) {
     TVZ_REQUIRE(cat && ws && ws->cat == cat, "workspace does not belong to this catalogue");
     TVZ_REQUIRE(qn >= 0 && (qn == 0 || h_q), "bad query");
-    if (!d_out) { d_out = ws->d_out; out_cap = ws->cap; }
+    if (!d_out) {
+        d_out = ws->d_out;
+        if (out_cap <= 0) out_cap = ws->cap;
+    }
     TVZ_REQUIRE(out_cap >= 1 && out_cap <= ws->cap, "output capacity %lld outside [1, %lld]", out_cap, ws->cap);
     int rc = ensure_query_capacity(ws, std::max(qn, 1));
     if (rc) return rc;
@@ -666,7 +716,7 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
         }
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
         rc = compact_enqueue(ws->d_counts, cat->n_rows, min_match, cat->d_vid, d_out, ws->d_rows, out_cap, ws->d_nhits,
-                             ws->d_state, ws->d_ticket, nullptr, nullptr, st);
+                             ws->d_state, ws->d_ticket, nullptr, nullptr, st, gather);
         if (rc) return rc;
         if (want_kth) {
             match_kth_kernel<<<2 * sms, 256, 0, st>>>(cat->d_ts, cat->d_off, ws->d_rows, d_out, out_cap,
@@ -674,6 +724,7 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
             TVZ_CUDA(cudaGetLastError());
         }
     } else {
+        TVZ_REQUIRE(!gather || gather->n_peers == 0, "an empty shard cannot take part in the fused gather");
         TVZ_CUDA(cudaMemsetAsync(d_out, 0, 8, st));
         TVZ_CUDA(cudaMemsetAsync(ws->d_nhits, 0, 8, st));
     }
@@ -707,6 +758,25 @@ int tvz_debug_match_count_ms(tvz_match_ws *ws, float *ms) {
 int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match,
                             int32_t *d_out, int64_t out_cap, void *stream) {
     return enqueue_match(cat, ws, h_q, qn, min_match, false, d_out, out_cap, static_cast<cudaStream_t>(stream));
+}
+
+int tvz_catalog_match_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn,
+                                   int min_match, int n_peers, const uint64_t *peer_record, const uint64_t *peer_flag,
+                                   const uint32_t *d_my_flags, int64_t out_cap, uint32_t epoch, void *stream) {
+    TVZ_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers, "n_peers %d outside [1, %d]", n_peers, kMaxPeers);
+    TVZ_REQUIRE(peer_record && peer_flag && d_my_flags, "null pointer");
+    TVZ_REQUIRE(cat && cat->n_rows > 0, "the fused gather needs a non-empty shard");
+    GatherTargets gt;
+    gt.n_peers = n_peers;
+    gt.epoch = epoch;
+    for (int p = 0; p < n_peers; ++p) {
+        gt.record[p] = reinterpret_cast<int *>(static_cast<uintptr_t>(peer_record[p]));
+        gt.flag[p] = reinterpret_cast<unsigned *>(static_cast<uintptr_t>(peer_flag[p]));
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = enqueue_match(cat, ws, h_q, qn, min_match, false, nullptr, out_cap, st, &gt);
+    if (rc) return rc;
+    return gather_wait_enqueue(d_my_flags, n_peers, epoch, st);
 }
 
 int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q, int qn, int min_match,

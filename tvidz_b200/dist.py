@@ -57,10 +57,15 @@ class ShardedCatalogue:
     ``match_async(q, min_match, out)`` filling an int32 [cap + 1, 2] record tensor on the
     rank's device.  The default is the CUDA `Catalogue` (no CPU path in the product; the
     gloo tests inject a CPU stand-in to exercise this host logic).
+
+    gather="nccl"  : one all_gather_into_tensor of the fixed-size records per query.
+    gather="fused" : the records live in symmetric (peer-mapped) memory and the compaction kernel
+                     itself stores each rank's record into every peer over NVLink and raises a
+                     flag; no collective launch on the data path (tvz_catalog_match_gather_async).
     """
 
     def __init__(self, ts, off, video_id, hit_capacity: int = 1 << 15, device=None,
-                 local_factory: Callable | None = None, group=None):
+                 local_factory: Callable | None = None, group=None, gather: str = "nccl"):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -75,29 +80,67 @@ class ShardedCatalogue:
         else:
             self.device = torch.device("cpu") if device is None else torch.device(device)
             self.local = local_factory(s_ts, s_off, s_vid)
+        if gather not in ("nccl", "fused"):
+            raise ValueError("gather must be 'nccl' or 'fused'")
+        if gather == "fused" and min(h - l for l, h in self.bounds) == 0:
+            gather = "nccl"                       # an empty shard cannot run the fused epilogue
+        self.gather = gather
         self.n_rows_local = hi - lo
         self.n_values_local = int(s_off[-1]) if s_off.size else 0
+        self.epoch = 0
         self._alloc(hit_capacity)
 
+    # ---- buffers -------------------------------------------------------------------------
     def _alloc(self, cap: int) -> None:
         self.cap = int(cap)
-        self.record = torch.zeros((self.cap + 1, 2), dtype=torch.int32, device=self.device)
-        self.gathered = torch.zeros((self.world * (self.cap + 1), 2), dtype=torch.int32, device=self.device)
+        rec = (self.cap + 1) * 2
+        if self.gather == "nccl":
+            self.record = torch.zeros((self.cap + 1, 2), dtype=torch.int32, device=self.device)
+            self.gathered = torch.zeros((self.world * (self.cap + 1), 2), dtype=torch.int32, device=self.device)
+            return
+        # fused: symmetric buffer = 2 sets x [world records] followed by 2 sets x [world flags]
+        import torch.distributed._symmetric_memory as symm
+        n_rec = 2 * self.world * rec
+        self.sym = symm.empty(n_rec + 2 * self.world + 32, dtype=torch.int32, device=self.device)
+        self.sym.zero_()
+        self.hdl = symm.rendezvous(self.sym, self.group if self.group is not None else dist.group.WORLD)
+        torch.cuda.synchronize(self.device)
+        self.hdl.barrier()
+        base = np.asarray([int(p) for p in self.hdl.buffer_ptrs], np.uint64)
+        self._peer_record, self._peer_flag, self._my_flags, self._views = [], [], [], []
+        for s in range(2):
+            self._peer_record.append(base + np.uint64(4 * (s * self.world * rec + self.rank * rec)))
+            self._peer_flag.append(base + np.uint64(4 * (n_rec + s * self.world + self.rank)))
+            self._my_flags.append(int(base[self.rank]) + 4 * (n_rec + s * self.world))
+            self._views.append(self.sym[s * self.world * rec:(s + 1) * self.world * rec].view(self.world, self.cap + 1, 2))
+        self.epoch = 0
 
-    def enqueue(self, new_timestamps, min_match: int) -> None:
-        """Local count + compaction, then the all-gather, all on the current stream."""
-        self.local.match_async(new_timestamps, min_match, self.record)
-        dist.all_gather_into_tensor(self.gathered, self.record, group=self.group)
+    def enqueue(self, new_timestamps, min_match: int) -> torch.Tensor:
+        """Local count + compaction + the gather, all on the current stream; returns the device
+        tensor [world, cap + 1, 2] that holds every shard's record once the stream gets there."""
+        if self.gather == "nccl":
+            self.local.match_async(new_timestamps, min_match, self.record)
+            dist.all_gather_into_tensor(self.gathered, self.record, group=self.group)
+            return self.gathered.view(self.world, self.cap + 1, 2)
+        self.epoch += 1
+        s = self.epoch & 1
+        self.local.match_gather_async(new_timestamps, min_match, self._peer_record[s], self._peer_flag[s],
+                                      self._my_flags[s], self.cap, self.epoch)
+        return self._views[s]
 
     def find_duplicates(self, new_timestamps, min_match: int = 5) -> list[tuple[int, int]]:
         """Every rank returns the full list [(video_id, match_count)] in catalogue order."""
         while True:
-            self.enqueue(new_timestamps, min_match)
-            pairs, overflow, needed = merge_records(
-                self.gathered.view(self.world, self.cap + 1, 2).cpu().numpy(), self.cap)
-            if not overflow:
-                return list(zip(pairs[:, 0].tolist(), pairs[:, 1].tolist()))
-            self._alloc(max(needed, 2 * self.cap))     # every rank sees the same records -> same decision
+            g = self.enqueue(new_timestamps, min_match)
+            heads = g[:, 0, :].cpu().numpy()                      # {n_hits, overflow} of every shard
+            n_max = int(heads[:, 0].max()) if heads.size else 0
+            if heads[:, 1].any() or n_max > self.cap:
+                if self.gather == "fused":
+                    self.hdl.barrier()                            # nobody still writes into the old buffers
+                self._alloc(max(n_max, 2 * self.cap))             # same records on every rank -> same decision
+                continue
+            pairs, _, _ = merge_records(g[:, :n_max + 1, :].cpu().numpy(), self.cap)
+            return list(zip(pairs[:, 0].tolist(), pairs[:, 1].tolist()))
 
 
 class ShardedFragmentCatalogue:
