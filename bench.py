@@ -329,7 +329,7 @@ def run_ours(args):
             n_values = cat.n_values
             local_cat = cat
         else:
-            sc = ShardedCatalogue(ts, off, vid, hit_capacity=cap, device=local)
+            sc = ShardedCatalogue(ts, off, vid, hit_capacity=cap, device=local, gather=args.gather)
             enqueue = lambda: sc.enqueue(q, mm)                                  # noqa: E731
             full = lambda: sc.find_duplicates(q, mm)                             # noqa: E731
             local_algo = sc.local.algo_bytes
@@ -368,8 +368,12 @@ def run_ours(args):
                     "config": {"workload": "configs[3]: one full-duplicate query against 1M synthetic "
                                            "cut-timestamp arrays, rows sharded over the GPUs",
                                "rows": CATALOGUE_ROWS, "values": int(off[-1]), "query_len": int(len(q)),
-                               "min_match": mm, "hits": len(hits), "collective": "all_gather of int32 "
-                               f"[{cap + 1},2] per-shard hit records" if world > 1 else "none",
+                               "min_match": mm, "hits": len(hits),
+                               "collective": "none" if world == 1 else (
+                                   "fused: the compaction kernel stores each shard's hit record into every peer "
+                                   "over NVLink (symmetric memory) and raises a flag; no NCCL call on the data path"
+                                   if args.gather == "fused" else
+                                   f"NCCL all_gather of int32 [{cap + 1},2] per-shard hit records"),
                                "catalogue_exceeds_l2": bool(local_algo > 126e6)},
                     "e2e": {"value": CATALOGUE_ROWS / (m_e2e * 1e-3), "unit": "pairs/s", "ms_per_query": m_e2e,
                             "h2d_bytes_per_step": int(len(q) * 8 * 2 + len(q) * 4),
@@ -496,6 +500,8 @@ def main():
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fragment", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="how the sharded matcher exchanges per-shard hit records at N > 1")
     args = ap.parse_args()
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
 

@@ -152,3 +152,53 @@ def test_full_size_properties(cuda):
     for s in (0, 37, 63):
         o_sad, _, _, _ = oracle.scene_batch(frames[s:s + 1].cpu().numpy())
         assert np.array_equal(sad[s:s + 1].cpu().numpy().astype(np.uint64), o_sad)
+
+
+@pytest.mark.parametrize("chunks", [[1, 1, 1, 37], [16, 16, 8], [40], [7, 0, 33], [39, 1]])
+def test_stream_scorer_equals_one_shot(cuda, chunks):
+    """Long-form video fed chunk by chunk (BASELINE config 3 shape: 4K frames) == one call."""
+    H, W = 2160, 3840
+    frames = synth.synth_frames(1, 40, H, W, seed=9, scene_len=(6, 13)).to(cuda)
+    sad, score, sel = scene.score_frames(frames)
+    sc = scene.StreamScorer()
+    got, t = [], 0
+    for n in chunks:
+        got.append(sc.feed(frames[0, t:t + n]))
+        t += n
+    assert t == 40 and sc.frames_seen == 40
+    assert torch.equal(torch.cat([g[0] for g in got], 1), sad)
+    assert torch.equal(torch.cat([g[1] for g in got], 1), score)
+    assert torch.equal(torch.cat([g[2] for g in got], 1), sel)
+    assert int(sel.sum()) >= 3
+    o_sad, o_score, o_sel, _ = oracle.scene_batch(frames.cpu().numpy())
+    assert np.array_equal(sad.cpu().numpy().astype(np.uint64), o_sad) and np.array_equal(sel.cpu().numpy(), o_sel)
+
+
+def test_config1_single_clip_end_to_end(cuda):
+    """BASELINE config 1: one 60 s 1080p30 clip through scene-cut detection (T = 0.3) and the compare
+    against 10 stored timestamp arrays -- the whole analyze_file path vs the oracle's."""
+    from oracle import match_oracle
+    from tvidz_b200.inspector import Inspector
+    frames = synth.synth_frames(1, 1800, 1080, 1920, seed=60, scene_len=(45, 240), device=cuda)
+    o_sad, o_score, o_sel, _ = oracle.scene_batch(frames.cpu().numpy())
+    want_cuts = oracle.cut_timestamps(o_sel[0])
+    assert 6 <= len(want_cuts) <= 40
+    assert scene.detect_scene_cuts(frames[0]) == want_cuts
+    rng = np.random.default_rng(60)
+    stored = [("v%d.mp4" % i, sorted(float("%.6g" % (n / 30)) for n in rng.integers(1, 1800, 12))) for i in range(9)]
+    stored.insert(4, ("original.mp4", list(want_cuts)))                 # the clip itself was uploaded before
+    ins = Inspector()
+    rows, names = [], {}
+    for fn, ts in stored:
+        v = ins.add_video(fn)
+        ins.add_timestamps(v.id, ts)
+        rows.append((v.id, ts))
+        names[v.id] = fn
+    res = ins.analyze_frames("uploads/1760000000000-original.mp4", frames[0])
+    o_scene, o_ids, o_names = match_oracle.streaming_analysis(rows, 11, want_cuts, 2, names)
+    assert res == {**match_oracle.result_record(o_scene, o_names, "1760000000000-original.mp4", "original.mp4"),
+                   "duplicates": res["duplicates"]}
+    assert set(res["duplicates"]) == set(o_names) == {"original.mp4"} and res["total_cuts"] == 2
+    fresh = ins.analyze_frames("other.mp4", synth.synth_frames(1, 300, 1080, 1920, seed=61, scene_len=(45, 90),
+                                                               device=cuda)[0])
+    assert fresh["status"] == "done" and fresh["duplicates"] == [] and fresh["total_cuts"] >= 2

@@ -298,36 +298,33 @@ match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, 
                 out[3 + 2 * pos] = cnt[j];
                 rows_out[pos] = r0 + j;
                 if (aux) aux_out[1 + pos] = aux[r0 + j];  // per-row payload (fragment mode: best offset)
+                // fused gather: every block ships its own hits to all peers (8-byte stores over NVLink)
+                for (int p = 0; p < gt.n_peers; ++p)
+                    *reinterpret_cast<int2 *>(gt.record[p] + 2 + 2 * pos) = make_int2(vid[r0 + j], cnt[j]);
             }
             ++pos;
         }
     }
     if (gt.n_peers == 0) return;
 
-    // ---- fused gather: the block that finishes last ships this rank's record to every peer ----
-    // (stores over NVLink into peer memory, then a system-scope release of the per-rank flag)
+    // ---- fused gather epilogue: the block that finishes last publishes the header and the flag ----
     __shared__ unsigned s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();  // this block's out[] writes (and the header, if it wrote it) before the count
+        __threadfence_system();  // this block's peer stores (and the local header) before it counts as done
         const unsigned done = atomicAdd(ticket + 2, 1u);
         s_last = done == gridDim.x - 1;
         if (s_last) ticket[2] = 0;
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
-    const long long hdr = *reinterpret_cast<volatile int *>(out);      // n_hits (saturated), written before
-    const int words = 2 * (1 + static_cast<int>(min(hdr, cap)));     // the header's block counted itself done
-    for (int p = 0; p < gt.n_peers; ++p) {
-        int *dst = gt.record[p];
-        if (dst == out) continue;  // single-GPU / self slot aliases the local record
-        for (int i = threadIdx.x; i < words; i += kScanThreads) dst[i] = __ldcg(out + i);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < gt.n_peers)
+    if (threadIdx.x < gt.n_peers) {
+        __threadfence_system();
+        const int2 hdr = make_int2(*reinterpret_cast<volatile int *>(out), *reinterpret_cast<volatile int *>(out + 1));
+        *reinterpret_cast<int2 *>(gt.record[threadIdx.x]) = hdr;  // {n_hits, overflow}
+        __threadfence_system();
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gt.flag[threadIdx.x]), "r"(gt.epoch) : "memory");
+    }
 }
 
 // Wait until every peer's record for `epoch` has landed in this rank's gather buffer.  Bounded:

@@ -130,6 +130,50 @@ def score_frames_host(frames, width: int | None = None, threshold: float = DEFAU
     return sad, score, sel
 
 
+class StreamScorer:
+    """Scores one or more concurrent streams chunk by chunk, as long-form video arrives (NVDEC
+    surfaces, a host ring buffer, ...): the reference's ffmpeg keeps only O(1) state per stream
+    -- the previous frame and prev_mafd (f_select.c get_scene_score) -- and so does this.
+
+    feed(chunk [S, n, H, P] or [n, H, P] on the GPU) returns (sad, score, selected) for exactly
+    those n frames, bit-identical to scoring the whole stream in one call.  Between chunks only
+    the last frame of each stream (one D2D copy) and its SAD are carried.
+    """
+
+    def __init__(self, threshold: float = DEFAULT_THRESHOLD, width: int | None = None):
+        self.threshold = float(threshold)
+        self.width = width
+        self._pair = None           # [S, 2, H, P]: slot 0 = carried frame, slot 1 = first frame of the new chunk
+        self._last_sad = None       # int64 [S]: SAD of the last frame fed (its mafd is the next prev_mafd)
+        self.frames_seen = 0
+
+    def feed(self, chunk: torch.Tensor):
+        chunk = _as_4d(chunk)
+        if not chunk.is_cuda:
+            raise ValueError("StreamScorer.feed takes GPU frames")
+        S, n, H, P = chunk.shape
+        if n == 0:
+            z = torch.zeros((S, 0), device=chunk.device)
+            return z.long(), z.double(), z.to(torch.uint8)
+        W = P if self.width is None else int(self.width)
+        sad = sad_luma(chunk, W)                                  # [S, n], column 0 = 0 for now
+        if self._pair is None:                                    # first chunk: frame 0 has no predecessor
+            self._pair = torch.empty((S, 2, H, P), dtype=torch.uint8, device=chunk.device)
+            score, sel = scene_select(sad, W, H, self.threshold)
+        else:
+            self._pair[:, 1].copy_(chunk[:, 0])
+            sad[:, 0] = sad_luma(self._pair, W)[:, 1]             # carried frame vs first new frame
+            # two leading columns: a dummy "frame 0", then the carried frame's SAD, whose mafd is the
+            # prev_mafd of this chunk's first frame (prev_mafd is updated on every frame, A.3)
+            ext = torch.cat([torch.zeros_like(sad[:, :1]), self._last_sad[:, None], sad], dim=1)
+            score, sel = scene_select(ext, W, H, self.threshold)
+            score, sel = score[:, 2:].contiguous(), sel[:, 2:].contiguous()
+        self._pair[:, 0].copy_(chunk[:, -1])
+        self._last_sad = sad[:, -1].clone()
+        self.frames_seen += n
+        return sad, score, sel
+
+
 # ------------------------------------------------------------------ timestamp text protocol
 def pts_time_string(pts: int, time_base: tuple[int, int] = (1, 30), fmt: str = "g6") -> str:
     """Text showinfo prints after ``pts_time:`` (libavutil/timestamp.h).
