@@ -113,6 +113,19 @@ int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q,
                       int32_t *out_video_id, int32_t *out_count, int32_t *out_kth,
                       int64_t cap, int64_t *n_out);
 
+/* Batched find_duplicates: the reference runs one analysis thread per upload (app.py:43,472), so
+ * concurrent queries are the normal case; up to 8 of them are answered by ONE pass over the
+ * catalogue (one bit per query in the filter map), more are processed group by group.
+ *   q_all / q_off : CSR of the queries (q_off has n_queries + 1 entries)
+ *   out_off       : int64 [n_queries + 1]; hits of query i are out_*[out_off[i] .. out_off[i+1])
+ * Each query may hold at most tvz_catalog_batch_limit() distinct values.  On TVZ_ERR_OVERFLOW
+ * *need_per_query (if > the workspace's hit_capacity) and *need_total say how much room a retry
+ * needs. */
+int tvz_catalog_batch_limit(void);
+int tvz_catalog_match_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all, const int64_t *q_off,
+                            int n_queries, int min_match, int32_t *out_video_id, int32_t *out_count,
+                            int64_t *out_off, int64_t cap_total, int64_t *need_per_query, int64_t *need_total);
+
 /* Device-resident variant for pipelines, CUDA graphs and the sharded matcher:
  * enqueues the query upload, the count kernel and the ordered compaction on
  * `stream` and returns without synchronising.  The result is written to

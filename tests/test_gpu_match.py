@@ -219,3 +219,28 @@ def test_reference_style_per_cut_loop_uses_the_overlay(cuda, stream_golden):
         small.add_timestamps(v.id, [float(i), float(i) + 0.5])
         assert small.find_duplicates([float(i), float(i) + 0.5], 2) == [(v.id, 2)]
     assert small.repacks == 2 and small.find_duplicates([0.0, 0.5, 3.0, 3.5], 2) == [(1, 2), (4, 2)]
+
+
+def test_batched_queries_equal_single_queries(cuda, match_golden):
+    """Up to 8 queries per catalogue pass: identical to one find_duplicates call per query."""
+    ts, off, vid = synth.synth_catalogue(120_000, seed=14)
+    cat = Catalogue(ts, off, vid, hit_capacity=64)              # tiny capacity: exercises the regrowth path
+    rng = np.random.default_rng(14)
+    queries = [ts[off[r]:off[r + 1]].copy() for r in rng.integers(0, 120_000, 19)]
+    queries += [np.zeros(0), np.array([float("nan"), 1.0, -0.0, 0.0]), np.array([5.0, 5.0, 5.0]),
+                np.unique(ts)[:400]]                             # empty, specials, repeats, too long for a batch
+    for mm in (2, 5, 0):
+        qs = queries if mm else queries[:3]
+        got = cat.find_duplicates_many(qs, mm)
+        assert len(got) == len(qs)
+        for q, g in zip(qs, got):
+            assert g == oracle.find_duplicates_csr(ts, off, vid, q, mm)
+    assert cat.find_duplicates_many([], 2) == []
+    cat.close()
+    for c in match_golden[:12]:                                  # the reference's own vectors, batched together
+        rows = _rows(c)
+        cat = Catalogue.from_rows(rows)
+        mm = 5 if c["min_match"] is None else c["min_match"]
+        got = cat.find_duplicates_many([c["query"]] * 3 + [[]], mm)
+        assert [list(x) for x in got[0]] == c["expected"] and got[0] == got[1] == got[2]
+        cat.close()

@@ -25,6 +25,9 @@ SYMBOLS = [
     ("tvz_match_ws_create", _i, [_vp, _i64, C.POINTER(_vp)]),
     ("tvz_match_ws_destroy", None, [_vp]),
     ("tvz_catalog_match", _i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
+    ("tvz_catalog_batch_limit", _i, []),
+    ("tvz_catalog_match_batch", _i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i64, C.POINTER(_i64),
+                                     C.POINTER(_i64)]),
     ("tvz_catalog_match_async", _i, [_vp, _vp, _vp, _i, _i, _vp, _i64, _vp]),
     ("tvz_catalog_match_gather_async", _i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64, C.c_uint32, _vp]),
     ("tvz_match_ws_hits", _vp, [_vp]),

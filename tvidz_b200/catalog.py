@@ -109,6 +109,49 @@ class Catalogue:
             return t.vid[:n].copy(), t.cnt[:n].copy(), t.kth[:n].copy()
         return t.vid[:n].copy(), t.cnt[:n].copy()
 
+    def match_many(self, queries, min_match: int = 5):
+        """Several find_duplicates queries at once -- up to 8 per pass over the catalogue.
+        -> list of (video_id i32 [n_i], match_count i32 [n_i]) per query, catalogue order.
+        Queries with more distinct values than the batch limit run through the single-query path."""
+        if self._handle is None:
+            raise RuntimeError("catalogue is closed")
+        qs = [np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(-1)) for q in queries]
+        limit = int(lib().tvz_catalog_batch_limit())
+        small = [i for i, q in enumerate(qs) if np.unique(q[~np.isnan(q)]).shape[0] <= limit]
+        results: list = [None] * len(qs)
+        for i in set(range(len(qs))) - set(small):
+            results[i] = self.match(qs[i], min_match)
+        if small:
+            q_off = np.zeros(len(small) + 1, np.int64)
+            np.cumsum([qs[i].shape[0] for i in small], out=q_off[1:])
+            q_all = np.concatenate([qs[i] for i in small]) if q_off[-1] else np.zeros(1, np.float64)
+            out_off = np.zeros(len(small) + 1, np.int64)
+            need_q, need_t = C.c_int64(0), C.c_int64(0)
+            cap_total, need = max(self.hit_capacity, 4096), 0
+            while True:
+                ws = self._ws(need)
+                vid = np.empty(cap_total, np.int32)
+                cnt = np.empty(cap_total, np.int32)
+                with torch.cuda.device(self.device):
+                    rc = lib().tvz_catalog_match_batch(self._handle, ws, q_all.ctypes.data, q_off.ctypes.data,
+                                                       len(small), int(min_match), vid.ctypes.data, cnt.ctypes.data,
+                                                       out_off.ctypes.data, cap_total, C.byref(need_q),
+                                                       C.byref(need_t))
+                if rc == TVZ_ERR_OVERFLOW:
+                    need = max(need, int(need_q.value))
+                    cap_total = max(cap_total, int(need_t.value))
+                    continue
+                check(rc)
+                break
+            for k, i in enumerate(small):
+                a, b = int(out_off[k]), int(out_off[k + 1])
+                results[i] = (vid[a:b].copy(), cnt[a:b].copy())
+        return results
+
+    def find_duplicates_many(self, queries, min_match: int = 5) -> list[list[tuple[int, int]]]:
+        """[find_duplicates(q, min_match) for q in queries], answered in batched catalogue passes."""
+        return [list(zip(v.tolist(), c.tolist())) for v, c in self.match_many(queries, min_match)]
+
     def match_async(self, new_timestamps, min_match: int, out: torch.Tensor, stream=None) -> None:
         """Enqueue one query on `stream` (default: torch's current stream) and return at once.
         `out`: int32 CUDA tensor [cap + 1, 2] receiving the fixed-size record described in

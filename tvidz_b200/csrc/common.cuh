@@ -25,6 +25,11 @@ struct GatherTargets {
     unsigned *flag[kMaxPeers] = {};  // this rank's flag word on peer p
 };
 
+// Batched compaction: blockIdx.y selects the query; per-query strides into the arrays.
+struct BatchStrides {
+    long long counts = 0, out = 0, rows = 0, state = 0;  // elements; ticket stride is 4 words, n_hits 1
+};
+
 // match.cu: single-pass ordered compaction shared by find_duplicates and fragment mode.
 // `ticket` holds three u32 {next ticket = 0, query epoch = 1, finished blocks = 0}.
 int compact_blocks(long long n_rows);
@@ -32,6 +37,9 @@ int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid
                     long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket,
                     const int *aux, int *aux_out, cudaStream_t st, const GatherTargets *gather = nullptr);
 int gather_wait_enqueue(const unsigned *d_flags, int n_peers, unsigned epoch, cudaStream_t st);
+int compact_enqueue_batch(int *counts, long long n_rows, int min_match, const int *vid, int *out, long long *rows_out,
+                          long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket, int n_batch,
+                          const BatchStrides &bs, cudaStream_t st);
 
 #define TVZ_CUDA(expr)                                                                        \
     do {                                                                                      \

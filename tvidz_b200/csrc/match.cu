@@ -174,6 +174,126 @@ match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
     drain();
 }
 
+// ---- batched queries: up to 8 find_duplicates calls answered by ONE pass over the catalogue ----
+// (the reference runs one analysis thread per upload, app.py:43,472, each calling find_duplicates:
+// concurrent queries are the normal case).  The byte map holds one bit per query, so one LDS.U8
+// says which of the 8 queries might contain a value; survivors carry that mask through the
+// per-warp queue and add into counts[query][row].
+constexpr int kBatch = 8;
+struct alignas(16) BatchSmem {
+    unsigned char map[kMapEntries];
+    unsigned long long keys[kBatch][kParamKeys];
+    unsigned long long qv[kCountWarps][kWarpQueue];
+    long long qe[kCountWarps][kWarpQueue];            // value index | query mask << 56
+    int mult[kBatch][kParamKeys];
+    int n_keys[kBatch];
+};
+
+__global__ void __launch_bounds__(kCountThreads, 2)
+match_count_batch_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
+                         const unsigned long long *__restrict__ keys, const int *__restrict__ mult,
+                         const int *__restrict__ n_keys, int n_batch, const long long *__restrict__ off,
+                         const int *__restrict__ block_row, long long n_rows, int *__restrict__ counts,
+                         long long counts_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BatchSmem &sm = *reinterpret_cast<BatchSmem *>(smem_raw);
+    for (int i = threadIdx.x; i < kMapEntries / 16; i += kCountThreads)
+        reinterpret_cast<uint4 *>(sm.map)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < kBatch) sm.n_keys[threadIdx.x] = threadIdx.x < n_batch ? n_keys[threadIdx.x] : 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_batch * kParamKeys; i += kCountThreads) {
+        const int b = i / kParamKeys, k = i - b * kParamKeys;
+        if (k < sm.n_keys[b]) {
+            const unsigned long long key = keys[i];
+            sm.keys[b][k] = key;
+            sm.mult[b][k] = mult[i];
+            // byte-wide atomic OR through the containing 32-bit word
+            const uint32_t h = filter_hash(key);
+            atomicOr(reinterpret_cast<unsigned *>(sm.map) + (h >> 2), (1u << b) << (8 * (h & 3)));
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    unsigned long long *qv = sm.qv[threadIdx.x >> 5];
+    long long *qe = sm.qe[threadIdx.x >> 5];
+    int queued = 0;  // warp-uniform
+
+    auto resolve = [&](unsigned long long v, long long packed) {
+        const long long elem = packed & ((1ll << 56) - 1);
+        unsigned qmask = static_cast<unsigned>(static_cast<unsigned long long>(packed) >> 56);
+        long long row = -1;
+        while (qmask) {
+            const int b = __ffs(qmask) - 1;
+            qmask &= qmask - 1;
+            int lo = 0, hi = sm.n_keys[b];
+            const int nk = hi;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (sm.keys[b][mid] < v) lo = mid + 1; else hi = mid;
+            }
+            if (lo >= nk || sm.keys[b][lo] != v) continue;  // filter false positive for this query
+            if (row < 0) {
+                const long long blk = elem >> kBlockShift;
+                long long a = block_row[blk], z = block_row[blk + 1] + 1;
+                while (z - a > 1) {
+                    const long long mid = (a + z) >> 1;
+                    if (off[mid] <= elem) a = mid; else z = mid;
+                }
+                row = a;
+            }
+            atomicAdd(&counts[b * counts_stride + row], sm.mult[b][lo]);
+        }
+    };
+    auto drain = [&]() {
+        __syncwarp();
+        for (int i = lane; i < min(queued, kWarpQueue); i += 32) resolve(qv[i], qe[i]);
+        __syncwarp();
+        queued = 0;
+    };
+    auto park = [&](unsigned m, unsigned long long x, long long elem) {
+        const unsigned mask = __ballot_sync(0xffffffffu, m != 0);
+        if (m) {
+            const int slot = queued + __popc(mask & ((1u << lane) - 1u));
+            const long long packed = elem | (static_cast<long long>(m) << 56);
+            if (slot < kWarpQueue) { qv[slot] = x; qe[slot] = packed; }
+            else resolve(x, packed);
+        }
+        queued += __popc(mask);
+    };
+
+    constexpr int kUnits = kCountUnroll / 2;
+    const long long stride = static_cast<long long>(gridDim.x) * kChunkPairs;
+    long long base = static_cast<long long>(blockIdx.x) * kChunkPairs;
+    const U64x4 *ts4 = reinterpret_cast<const U64x4 *>(ts2);
+    U64x4 v[kUnits];
+    if (base < n_pairs_padded) {
+#pragma unroll
+        for (int j = 0; j < kUnits; ++j) v[j] = ld_stream_256(ts4 + (base >> 1) + j * kCountThreads + threadIdx.x);
+    }
+    for (; base < n_pairs_padded; base += stride) {
+        const bool more = base + stride < n_pairs_padded;
+        const U64x4 *next = ts4 + ((base + stride) >> 1) + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < kUnits; ++j) {
+            const unsigned ma = sm.map[filter_hash(v[j].a)], mb = sm.map[filter_hash(v[j].b)];
+            const unsigned mc = sm.map[filter_hash(v[j].c)], md = sm.map[filter_hash(v[j].d)];
+            const unsigned any = __reduce_or_sync(0xffffffffu, (ma != 0) | ((mb != 0) << 1) | ((mc != 0) << 2) |
+                                                                   ((md != 0) << 3));
+            if (any) {
+                const long long elem = 2 * base + 4 * (j * kCountThreads + threadIdx.x);
+                if (any & 1u) park(ma, v[j].a, elem);
+                if (any & 2u) park(mb, v[j].b, elem + 1);
+                if (any & 4u) park(mc, v[j].c, elem + 2);
+                if (any & 8u) park(md, v[j].d, elem + 3);
+                if (queued >= kWarpQueue / 2) drain();
+            }
+            if (more) v[j] = ld_stream_256(next + j * kCountThreads);
+        }
+    }
+    drain();
+}
+
 // Ordered compaction of the rows with counts[row] >= min_match, in ONE pass (decoupled
 // look-back): a block takes a ticket (so tickets start in order), counts its qualifying rows,
 // publishes {epoch, AGGREGATE, n}, sums its predecessors' records walking backwards 32 at a
@@ -196,7 +316,15 @@ __global__ void __launch_bounds__(kScanThreads)
 match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, const int *__restrict__ vid,
                      int *__restrict__ out, long long *__restrict__ rows_out, long long cap,
                      long long *__restrict__ n_hits_out, unsigned long long *state, unsigned *ticket,
-                     const int *__restrict__ aux, int *__restrict__ aux_out, const __grid_constant__ GatherTargets gt) {
+                     const int *__restrict__ aux, int *__restrict__ aux_out, const __grid_constant__ GatherTargets gt,
+                     const BatchStrides bs) {
+    // batched queries: blockIdx.y picks the query, everything below is per query
+    counts += blockIdx.y * bs.counts;
+    out += blockIdx.y * bs.out;
+    rows_out += blockIdx.y * bs.rows;
+    state += blockIdx.y * bs.state;
+    ticket += blockIdx.y * 4;
+    n_hits_out += blockIdx.y;
     // ticket[0] = next ticket, ticket[1] = query epoch.  The epoch is read BEFORE the ticket is
     // taken and bumped by the holder of the last ticket, i.e. after every block has read it:
     // the kernel is self-contained and can be replayed from a CUDA graph.
@@ -383,7 +511,18 @@ int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid
     const GatherTargets none{};
     match_compact_kernel<<<compact_blocks(n_rows), kScanThreads, 0, st>>>(counts, n_rows, min_match, vid, out, rows_out,
                                                                           cap, n_hits_out, state, ticket, aux, aux_out,
-                                                                          gather ? *gather : none);
+                                                                          gather ? *gather : none, BatchStrides{});
+    TVZ_CUDA(cudaGetLastError());
+    return TVZ_OK;
+}
+
+int compact_enqueue_batch(int *counts, long long n_rows, int min_match, const int *vid, int *out, long long *rows_out,
+                          long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket, int n_batch,
+                          const BatchStrides &bs, cudaStream_t st) {
+    const GatherTargets none{};
+    dim3 grid(compact_blocks(n_rows), n_batch);
+    match_compact_kernel<<<grid, kScanThreads, 0, st>>>(counts, n_rows, min_match, vid, out, rows_out, cap, n_hits_out,
+                                                        state, ticket, nullptr, nullptr, none, bs);
     TVZ_CUDA(cudaGetLastError());
     return TVZ_OK;
 }
@@ -432,6 +571,14 @@ struct tvz_match_ws {
     bool stage_busy = false;
     bool timing = false;           // debug: bracket the count kernel(s) with events
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // batched queries (allocated on first use): per-query copies of counts/out/rows/state/ticket
+    int *b_counts = nullptr, *b_out = nullptr, *b_mult = nullptr, *b_nkeys = nullptr;
+    long long *b_rows = nullptr, *b_nhits = nullptr;
+    unsigned long long *b_state = nullptr, *b_keys = nullptr;
+    unsigned *b_ticket = nullptr;
+    uint8_t *hb_stage = nullptr;   // pinned: keys | mult | n_keys
+    int *hb_out = nullptr;         // pinned [8][cap+1][2]
+    long long hb_cap = 0;
 };
 
 namespace {
@@ -624,6 +771,12 @@ void tvz_match_ws_destroy(tvz_match_ws *ws) {
     if (ws->h_stage) cudaFreeHost(ws->h_stage);
     if (ws->h_out) cudaFreeHost(ws->h_out);
     if (ws->h_kth) cudaFreeHost(ws->h_kth);
+    void *bdev[] = {ws->b_counts, ws->b_out, ws->b_mult, ws->b_nkeys, ws->b_rows, ws->b_nhits, ws->b_state, ws->b_keys,
+                    ws->b_ticket};
+    for (void *p : bdev)
+        if (p) cudaFree(p);
+    if (ws->hb_stage) cudaFreeHost(ws->hb_stage);
+    if (ws->hb_out) cudaFreeHost(ws->hb_out);
     if (ws->staged) cudaEventDestroy(ws->staged);
     if (ws->t0) cudaEventDestroy(ws->t0);
     if (ws->t1) cudaEventDestroy(ws->t1);
@@ -811,6 +964,151 @@ int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q,
         out_count[h] = ws->h_out[3 + 2 * h];
     }
     if (out_kth) memcpy(out_kth, ws->h_kth, n_hits * 4);
+    return TVZ_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int ensure_batch_buffers(tvz_match_ws *ws) {
+    const tvz_catalog *cat = ws->cat;
+    if (ws->b_counts && ws->hb_cap == ws->cap) return TVZ_OK;
+    TVZ_REQUIRE(!ws->b_counts, "batch buffers cannot be resized");  // cap is fixed per workspace
+    const size_t nr = std::max<long long>(1, cat->n_rows);
+    const size_t nb = std::max(1, ws->n_blocks);
+    TVZ_CUDA(cudaMalloc(&ws->b_counts, kBatch * nr * 4));
+    TVZ_CUDA(cudaMemset(ws->b_counts, 0, kBatch * nr * 4));
+    TVZ_CUDA(cudaMalloc(&ws->b_out, kBatch * (ws->cap + 1) * 8));
+    TVZ_CUDA(cudaMalloc(&ws->b_rows, kBatch * ws->cap * 8));
+    TVZ_CUDA(cudaMalloc(&ws->b_nhits, kBatch * 8));
+    TVZ_CUDA(cudaMalloc(&ws->b_state, kBatch * nb * 8));
+    TVZ_CUDA(cudaMemset(ws->b_state, 0, kBatch * nb * 8));
+    TVZ_CUDA(cudaMalloc(&ws->b_ticket, kBatch * 16));
+    unsigned init[kBatch * 4];
+    for (int b = 0; b < kBatch; ++b) { init[4 * b] = 0; init[4 * b + 1] = 1; init[4 * b + 2] = 0; init[4 * b + 3] = 0; }
+    TVZ_CUDA(cudaMemcpy(ws->b_ticket, init, sizeof init, cudaMemcpyHostToDevice));
+    TVZ_CUDA(cudaMalloc(&ws->b_keys, kBatch * kParamKeys * 8));
+    TVZ_CUDA(cudaMalloc(&ws->b_mult, kBatch * kParamKeys * 4));
+    TVZ_CUDA(cudaMalloc(&ws->b_nkeys, kBatch * 4));
+    TVZ_CUDA(cudaHostAlloc(&ws->hb_stage, kBatch * kParamKeys * 12 + kBatch * 4, cudaHostAllocDefault));
+    TVZ_CUDA(cudaHostAlloc(&ws->hb_out, kBatch * (ws->cap + 1) * 8, cudaHostAllocDefault));
+    TVZ_CUDA(cudaDeviceSynchronize());
+    ws->hb_cap = ws->cap;
+    return TVZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tvz_catalog_batch_limit(void) { return kParamKeys; }
+
+/* Up to 8 queries per catalogue pass; more are processed group by group.  Queries with more than
+ * tvz_catalog_batch_limit() distinct values are refused (run them through tvz_catalog_match). */
+int tvz_catalog_match_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all, const int64_t *q_off,
+                            int n_queries, int min_match, int32_t *out_video_id, int32_t *out_count,
+                            int64_t *out_off, int64_t cap_total, int64_t *need_per_query, int64_t *need_total_out) {
+    TVZ_REQUIRE(cat && ws && ws->cat == cat, "workspace does not belong to this catalogue");
+    TVZ_REQUIRE(n_queries >= 0 && q_off && out_off && need_per_query && need_total_out, "bad arguments");
+    *need_per_query = 0;
+    *need_total_out = 0;
+    TVZ_REQUIRE(cap_total >= 0 && (cap_total == 0 || (out_video_id && out_count)), "bad output buffers");
+    out_off[0] = 0;
+    if (n_queries == 0) return TVZ_OK;
+    int rc = ensure_batch_buffers(ws);
+    if (rc) return rc;
+    cudaStream_t st = ws->stream;
+    unsigned long long *h_keys = reinterpret_cast<unsigned long long *>(ws->hb_stage);
+    int *h_mult = reinterpret_cast<int *>(h_keys + kBatch * kParamKeys);
+    int *h_nk = h_mult + kBatch * kParamKeys;
+    const long long rec = (ws->cap + 1) * 2;
+    long long written = 0;
+    bool overflow = false;
+    long long need_cap = 0, need_total = 0;
+    std::vector<unsigned long long> sorted;
+    for (int g0 = 0; g0 < n_queries; g0 += kBatch) {
+        const int nb = std::min(kBatch, n_queries - g0);
+        for (int b = 0; b < nb; ++b) {
+            const double *q = q_all + q_off[g0 + b];
+            const long long qn = q_off[g0 + b + 1] - q_off[g0 + b];
+            TVZ_REQUIRE(qn >= 0, "query offsets must be non-decreasing");
+            sorted.clear();
+            for (long long i = 0; i < qn; ++i) {
+                const unsigned long long bits = canon_bits(q[i]);
+                if (!is_nan_bits(bits)) sorted.push_back(bits);
+            }
+            std::sort(sorted.begin(), sorted.end());
+            int nk = 0;
+            for (size_t i = 0; i < sorted.size();) {
+                size_t j = i;
+                while (j < sorted.size() && sorted[j] == sorted[i]) ++j;
+                TVZ_REQUIRE(nk < kParamKeys, "query %d has more than %d distinct values: not batchable", g0 + b,
+                            kParamKeys);
+                h_keys[b * kParamKeys + nk] = sorted[i];
+                h_mult[b * kParamKeys + nk] = static_cast<int>(j - i);
+                ++nk;
+                i = j;
+            }
+            h_nk[b] = nk;
+        }
+        if (cat->n_rows > 0) {
+            TVZ_CUDA(cudaMemcpyAsync(ws->b_keys, h_keys, kBatch * kParamKeys * 8, cudaMemcpyHostToDevice, st));
+            TVZ_CUDA(cudaMemcpyAsync(ws->b_mult, h_mult, kBatch * kParamKeys * 4, cudaMemcpyHostToDevice, st));
+            TVZ_CUDA(cudaMemcpyAsync(ws->b_nkeys, h_nk, kBatch * 4, cudaMemcpyHostToDevice, st));
+            TVZ_CUDA(cudaFuncSetAttribute(match_count_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(sizeof(BatchSmem))));
+            const long long chunks = cat->n_pairs_padded / kChunkPairs;
+            const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, 2ll * num_sms())));
+            if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
+            match_count_batch_kernel<<<grid, kCountThreads, sizeof(BatchSmem), st>>>(
+                reinterpret_cast<const ulonglong2 *>(cat->d_ts), cat->n_pairs_padded, ws->b_keys, ws->b_mult, ws->b_nkeys,
+                nb, cat->d_off, cat->d_block_row, cat->n_rows, ws->b_counts, cat->n_rows);
+            TVZ_CUDA(cudaGetLastError());
+            if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
+            BatchStrides bs;
+            bs.counts = cat->n_rows;
+            bs.out = rec;
+            bs.rows = ws->cap;
+            bs.state = std::max(1, ws->n_blocks);
+            rc = compact_enqueue_batch(ws->b_counts, cat->n_rows, min_match, cat->d_vid, ws->b_out, ws->b_rows, ws->cap,
+                                       ws->b_nhits, ws->b_state, ws->b_ticket, nb, bs, st);
+            if (rc) return rc;
+            // headers of the group in one strided copy, then each query's hits
+            TVZ_CUDA(cudaMemcpy2DAsync(ws->hb_out, rec * 4, ws->b_out, rec * 4, 8, nb, cudaMemcpyDeviceToHost, st));
+            TVZ_CUDA(cudaStreamSynchronize(st));
+            for (int b = 0; b < nb; ++b) {
+                const long long n = ws->hb_out[b * rec];
+                if (n > ws->cap) { overflow = true; need_cap = std::max(need_cap, n); continue; }
+                if (n > 0)
+                    TVZ_CUDA(cudaMemcpyAsync(ws->hb_out + b * rec + 2, ws->b_out + b * rec + 2, n * 8,
+                                             cudaMemcpyDeviceToHost, st));
+            }
+            TVZ_CUDA(cudaStreamSynchronize(st));
+        } else {
+            for (int b = 0; b < nb; ++b) ws->hb_out[b * rec] = 0;
+        }
+        for (int b = 0; b < nb; ++b) {
+            const long long n = std::min<long long>(ws->hb_out[b * rec], ws->cap);
+            need_total += ws->hb_out[b * rec];
+            if (!overflow && written + n <= cap_total) {
+                for (long long h = 0; h < n; ++h) {
+                    out_video_id[written + h] = ws->hb_out[b * rec + 2 + 2 * h];
+                    out_count[written + h] = ws->hb_out[b * rec + 3 + 2 * h];
+                }
+                written += n;
+            } else {
+                overflow = true;
+            }
+            out_off[g0 + b + 1] = written;
+        }
+    }
+    *need_per_query = need_cap;
+    *need_total_out = need_total;
+    if (overflow) {
+        return set_error(TVZ_ERR_OVERFLOW, "batch results need %lld entries in total (caller gave %lld) and %lld per "
+                         "query (workspace holds %lld)", need_total, (long long)cap_total, need_cap, ws->cap);
+    }
     return TVZ_OK;
 }
 
