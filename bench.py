@@ -420,6 +420,28 @@ def run_ours(args):
                                          + (" + all_gather)" if world > 1 else ")"),
                                  "peak_source": peak_src},
                     "gpu_launches_per_query": 3}
+        if world == 1:
+            # 64 concurrent analyses (one per stream of configs[1]) asking at once: 8 queries per catalogue pass
+            rng = np.random.default_rng(7)
+            qs = [ts[off[r]:off[r + 1]].copy() for r in rng.integers(0, CATALOGUE_ROWS, 64)]
+            many = cat.find_duplicates_many(qs, mm)
+            assert many[5] == cat.find_duplicates(qs[5], mm)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                cat.match_many(qs, mm)
+            b_s = (time.perf_counter() - t0) / reps
+            cat.debug_count_kernel_ms(True)
+            cat.match_many(qs[:8], mm)
+            b_kernel_ms = cat.debug_count_kernel_ms()
+            cat.debug_count_kernel_ms(False)
+            matching["batched"] = {"queries": 64, "queries_per_pass": 8, "value": 64 * CATALOGUE_ROWS / b_s,
+                                   "unit": "pairs/s", "ms_per_64_queries": 1e3 * b_s,
+                                   "count_kernel_ms_per_pass": b_kernel_ms,
+                                   "kernel_pairs_per_s": 8 * CATALOGUE_ROWS / (b_kernel_ms * 1e-3),
+                                   "path": "Catalogue.match_many: host queries in, numpy hit arrays out (host<->device "
+                                           "copies and synchronisation inside the timed region)",
+                                   "hits_total": int(sum(len(m) for m in many))}
         if rank == 0 and not args.no_cpu:
             matching["cpu_baseline"] = cpu_matching_baseline(ts, off, vid, q, mm, PYTHON_MATCH_SAMPLE_ROWS)
 
