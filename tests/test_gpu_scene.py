@@ -202,3 +202,35 @@ def test_config1_single_clip_end_to_end(cuda):
     fresh = ins.analyze_frames("other.mp4", synth.synth_frames(1, 300, 1080, 1920, seed=61, scene_len=(45, 90),
                                                                device=cuda)[0])
     assert fresh["status"] == "done" and fresh["duplicates"] == [] and fresh["total_cuts"] >= 2
+
+
+def test_random_shapes_and_strides(cuda):
+    """Hypothesis-style sweep: 48 seeded random geometries (odd widths, padded pitches, frame and
+    stream strides with gaps, aligned and unaligned bases) -- every path must give the oracle's integers."""
+    rng = np.random.default_rng(2026)
+    paths = set()
+    for case in range(48):
+        S, F = int(rng.integers(1, 5)), int(rng.integers(1, 12))
+        H = int(rng.integers(1, 70))
+        W = int(rng.choice([1, 7, 16, 31, 48, 64, 100, 128, 240, 333, 1024, 1920]))
+        kind = case % 4
+        P = W if kind == 0 else W + int(rng.choice([0, 1, 16, 32, 13]))
+        if kind == 2:
+            P = (W + 15) // 16 * 16 + 16 * int(rng.integers(0, 3))          # 16-byte aligned pitch
+        fgap = int(rng.choice([0, 16, 48])) if kind != 3 else int(rng.integers(0, 9))
+        sgap = int(rng.choice([0, 32, 256])) if kind != 3 else int(rng.integers(0, 9))
+        base_off = 0 if kind != 3 else int(rng.integers(0, 16))
+        fstride = H * P + fgap
+        sstride = F * fstride + sgap
+        total = base_off + S * sstride + 64
+        buf = torch.from_numpy(rng.integers(0, 256, total, dtype=np.uint8))
+        view = buf[base_off:].as_strided((S, F, H, P), (sstride, fstride, P, 1))
+        dense = np.ascontiguousarray(view.numpy())
+        o_sad, o_score, o_sel, _ = oracle.scene_batch(dense, W)
+        dbuf = buf.to(cuda)
+        dview = dbuf[base_off:].as_strided((S, F, H, P), (sstride, fstride, P, 1))
+        paths.add(L.lib().tvz_sad_luma_u8_path(dview.data_ptr(), W, H, P, fstride, sstride))
+        sad, score, sel = scene.score_frames(dview, W)
+        assert np.array_equal(sad.cpu().numpy().astype(np.uint64), o_sad), (case, S, F, H, W, P, fstride, sstride)
+        assert np.array_equal(score.cpu().numpy(), o_score) and np.array_equal(sel.cpu().numpy(), o_sel)
+    assert paths == {0, 1}
