@@ -56,6 +56,13 @@ int tvz_sad_luma_u8(const uint8_t *d_luma, int n_streams, int n_frames, int widt
                     int64_t pitch_bytes, int64_t frame_stride_bytes, int64_t stream_stride_bytes,
                     uint64_t *d_sad, void *stream);
 
+/* The same for planes of 16-bit samples (FFmpeg scene_sad.c ff_scene_sad16_c, the path the select
+ * filter takes for yuv420p10): `width` in samples, pitch and strides in bytes.  Follow with
+ * tvz_scene_select(..., bitdepth = 10), which divides mafd by 2^(bitdepth-8) as f_select.c does. */
+int tvz_sad_luma_u16(const uint16_t *d_luma, int n_streams, int n_frames, int width, int height,
+                     int64_t pitch_bytes, int64_t frame_stride_bytes, int64_t stream_stride_bytes,
+                     uint64_t *d_sad, void *stream);
+
 /* Which kernel tvz_sad_luma_u8 would pick for this layout: 1 = TMA bulk, 0 = generic. */
 int tvz_sad_luma_u8_path(const uint8_t *d_luma, int width, int height, int64_t pitch_bytes,
                          int64_t frame_stride_bytes, int64_t stream_stride_bytes);
@@ -75,7 +82,8 @@ int tvz_scene_select(const uint64_t *d_sad, int n_streams, int n_frames, int wid
  * frames sit in (ideally pinned) host memory.  Frames are streamed to the device
  * in chunks over two copy/compute streams, scored, and the three result arrays
  * [n_streams][n_frames] are written back to host memory.  Any of h_sad, h_score,
- * h_selected may be NULL.  chunk_frames <= 0 picks a default.
+ * h_selected may be NULL.  chunk_frames <= 0 picks a default.  bitdepth 8: h_luma holds bytes;
+ * bitdepth 9..16: h_luma holds 16-bit samples (width in samples, pitch/strides in bytes).
  */
 int tvz_scene_score_host(const uint8_t *h_luma, int n_streams, int n_frames, int width, int height,
                          int64_t pitch_bytes, int64_t frame_stride_bytes, int64_t stream_stride_bytes,

@@ -105,15 +105,17 @@ def _p(a: np.ndarray):
 # ---------------------------------------------------------------- stage 1
 def scene_batch(luma: np.ndarray, width: int | None = None, threshold: float = 0.3,
                 bitdepth: int = 8, n_threads: int = 0):
-    """luma: uint8 [S, F, H, P] (P = pitch >= width).  Returns (sad u64 [S,F],
-    score f64 [S,F], selected u8 [S,F], threads_used)."""
-    assert luma.dtype == np.uint8 and luma.ndim == 4 and luma.flags.c_contiguous
+    """luma: uint8 (bitdepth 8) or uint16 (bitdepth 9..16) [S, F, H, P] (P = pitch in samples >= width).
+    Returns (sad u64 [S,F], score f64 [S,F], selected u8 [S,F], threads_used)."""
+    assert luma.dtype in (np.uint8, np.uint16) and luma.ndim == 4 and luma.flags.c_contiguous
+    assert (luma.dtype == np.uint8) == (bitdepth == 8)
     S, F, H, P = luma.shape
     W = P if width is None else width
+    b = luma.dtype.itemsize
     sad = np.zeros((S, F), np.uint64)
     score = np.zeros((S, F), np.float64)
     sel = np.zeros((S, F), np.uint8)
-    used = lib().tvzo_scene_batch(_p(luma), S, F, W, H, P, H * P, F * H * P, bitdepth, threshold,
+    used = lib().tvzo_scene_batch(_p(luma), S, F, W, H, P * b, H * P * b, F * H * P * b, bitdepth, threshold,
                                   _p(sad), _p(score), _p(sel), n_threads)
     return sad, score, sel, used
 

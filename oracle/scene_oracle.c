@@ -48,6 +48,23 @@ uint64_t tvzo_scene_sad_u8(const uint8_t *prev, int64_t prev_pitch,
     return sad;
 }
 
+/* ff_scene_sad16_c (libavfilter/scene_sad.c): the same over 16-bit samples -- the routine the
+ * select filter installs when bitdepth > 8 (yuv420p10).  width in samples, pitches in bytes. */
+uint64_t tvzo_scene_sad_u16(const uint8_t *prev, int64_t prev_pitch, const uint8_t *cur, int64_t cur_pitch,
+                            int width, int height)
+{
+    uint64_t sad = 0;
+    for (int y = 0; y < height; y++) {
+        const uint16_t *a = (const uint16_t *)(prev + (int64_t)y * prev_pitch);
+        const uint16_t *b = (const uint16_t *)(cur + (int64_t)y * cur_pitch);
+        for (int x = 0; x < width; x++) {
+            int d = (int)a[x] - (int)b[x];
+            sad += (uint64_t)(d < 0 ? -d : d);
+        }
+    }
+    return sad;
+}
+
 /* av_clipf_c (libavutil/common.h): float in, float out. */
 static float clipf(float a, float amin, float amax)
 {
@@ -90,9 +107,8 @@ void tvzo_scene_stream(const uint8_t *luma, int n_frames, int width, int height,
     if (n_frames <= 0) return;
     sad_out[0] = 0;
     for (int t = 1; t < n_frames; t++)
-        sad_out[t] = tvzo_scene_sad_u8(luma + (int64_t)(t - 1) * frame_stride, pitch,
-                                       luma + (int64_t)t * frame_stride, pitch,
-                                       width, height);
+        sad_out[t] = (bitdepth > 8 ? tvzo_scene_sad_u16 : tvzo_scene_sad_u8)(
+            luma + (int64_t)(t - 1) * frame_stride, pitch, luma + (int64_t)t * frame_stride, pitch, width, height);
     tvzo_scene_scores(sad_out, n_frames, width, height, bitdepth, threshold,
                       score, selected);
 }

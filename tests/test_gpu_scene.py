@@ -234,3 +234,25 @@ def test_random_shapes_and_strides(cuda):
         assert np.array_equal(sad.cpu().numpy().astype(np.uint64), o_sad), (case, S, F, H, W, P, fstride, sstride)
         assert np.array_equal(score.cpu().numpy(), o_score) and np.array_equal(sel.cpu().numpy(), o_sel)
     assert paths == {0, 1}
+
+
+@pytest.mark.parametrize("S,F,H,W,P", [(2, 6, 40, 64, 64), (1, 4, 1080, 1920, 1920), (3, 5, 33, 100, 104),
+                                       (2, 7, 17, 63, 63), (1, 3, 2160, 3840, 3840)])
+def test_ten_bit_luma(cuda, S, F, H, W, P):
+    """yuv420p10: 16-bit samples through ff_scene_sad16_c's arithmetic and mafd / 4 (A.1, A.3)."""
+    rng = np.random.default_rng(W + F)
+    f = rng.integers(0, 1024, (S, F, H, P), dtype=np.uint16)
+    f[:, F // 2:] = np.clip(f[:, F // 2:].astype(np.int32) + 300, 0, 1023).astype(np.uint16)   # a cut
+    o_sad, o_score, o_sel, _ = oracle.scene_batch(f, W, bitdepth=10)
+    d = torch.from_numpy(f.view(np.int16)).to(cuda)
+    sad, score, sel = scene.score_frames(d, W, bitdepth=10)
+    assert np.array_equal(sad.cpu().numpy().astype(np.uint64), o_sad)
+    assert np.array_equal(score.cpu().numpy(), o_score) and np.array_equal(sel.cpu().numpy(), o_sel)
+    h_sad, h_score, h_sel = scene.score_frames_host(f, W, bitdepth=10, chunk_frames=3)
+    assert np.array_equal(h_sad, o_sad) and np.array_equal(h_score, o_score) and np.array_equal(h_sel, o_sel)
+    assert o_sel.sum() >= S
+    # full-scale KAT: 0 -> 1023 everywhere is mafd 1023/4 = 255.75 -> score clips to 1.0
+    k = np.zeros((1, 2, 8, 16), np.uint16)
+    k[0, 1] = 1023
+    sad, score, sel = scene.score_frames(torch.from_numpy(k.view(np.int16)).to(cuda), bitdepth=10)
+    assert sad.tolist() == [[0, 1023 * 128]] and score.tolist() == [[0.0, 1.0]]

@@ -14,6 +14,7 @@ SYMBOLS = [
     ("tvz_last_error", C.c_char_p, []),
     ("tvz_abi_version", _i, []),
     ("tvz_sad_luma_u8", _i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _vp]),
+    ("tvz_sad_luma_u16", _i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _vp]),
     ("tvz_sad_luma_u8_path", _i, [_vp, _i, _i, _i64, _i64, _i64]),
     ("tvz_scene_select", _i, [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp]),
     ("tvz_scene_score_host", _i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i, _d, _i, _vp, _vp, _vp]),

@@ -41,6 +41,24 @@ int compact_enqueue_batch(int *counts, long long n_rows, int min_match, const in
                           long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket, int n_batch,
                           const BatchStrides &bs, cudaStream_t st);
 
+}  // namespace tvz
+#include <exception>
+#include <new>
+namespace tvz {
+// The C ABI never throws: host-side allocation failures become TVZ_ERR_NOMEM.
+template <class F>
+int guarded(F &&body) noexcept {
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        return set_error(TVZ_ERR_NOMEM, "out of host memory");
+    } catch (const std::exception &e) {
+        return set_error(TVZ_ERR_INVALID, "unexpected exception: %s", e.what());
+    } catch (...) {
+        return set_error(TVZ_ERR_INVALID, "unexpected exception");
+    }
+}
+
 #define TVZ_CUDA(expr)                                                                        \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \

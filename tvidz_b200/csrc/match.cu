@@ -617,6 +617,7 @@ extern "C" {
 
 int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_video_id, int64_t n_rows,
                        tvz_catalog **out) {
+    return guarded([&]() -> int {
     TVZ_REQUIRE(out, "null out pointer");
     *out = nullptr;
     TVZ_REQUIRE(n_rows >= 0, "negative n_rows");
@@ -691,6 +692,7 @@ int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *
         return fail(e, "cudaMemcpy(vid)");
     *out = c;
     return TVZ_OK;
+    });
 }
 
 void tvz_catalog_destroy(tvz_catalog *c) {
@@ -707,6 +709,7 @@ int64_t tvz_catalog_values(const tvz_catalog *c) { return c ? c->n_vals : 0; }
 int64_t tvz_catalog_algo_bytes(const tvz_catalog *c) { return c ? 8 * c->n_vals + 8 * (c->n_rows + 1) : 0; }
 
 int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_ws **out) {
+    return guarded([&]() -> int {
     TVZ_REQUIRE(cat && out, "null pointer");
     *out = nullptr;
     TVZ_REQUIRE(hit_capacity >= 0, "negative capacity");
@@ -753,6 +756,7 @@ int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail(e, "cudaDeviceSynchronize");
     *out = ws;
     return TVZ_OK;
+    });
 }
 
 void tvz_match_ws_destroy(tvz_match_ws *ws) {
@@ -907,12 +911,15 @@ int tvz_debug_match_count_ms(tvz_match_ws *ws, float *ms) {
 
 int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match,
                             int32_t *d_out, int64_t out_cap, void *stream) {
+    return guarded([&]() -> int {
     return enqueue_match(cat, ws, h_q, qn, min_match, false, d_out, out_cap, static_cast<cudaStream_t>(stream));
+    });
 }
 
 int tvz_catalog_match_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn,
                                    int min_match, int n_peers, const uint64_t *peer_record, const uint64_t *peer_flag,
                                    const uint32_t *d_my_flags, int64_t out_cap, uint32_t epoch, void *stream) {
+    return guarded([&]() -> int {
     TVZ_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers, "n_peers %d outside [1, %d]", n_peers, kMaxPeers);
     TVZ_REQUIRE(peer_record && peer_flag && d_my_flags, "null pointer");
     TVZ_REQUIRE(cat && cat->n_rows > 0, "the fused gather needs a non-empty shard");
@@ -927,10 +934,12 @@ int tvz_catalog_match_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, con
     int rc = enqueue_match(cat, ws, h_q, qn, min_match, false, nullptr, out_cap, st, &gt);
     if (rc) return rc;
     return gather_wait_enqueue(d_my_flags, n_peers, epoch, st);
+    });
 }
 
 int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q, int qn, int min_match,
                       int32_t *out_video_id, int32_t *out_count, int32_t *out_kth, int64_t cap, int64_t *n_out) {
+    return guarded([&]() -> int {
     TVZ_REQUIRE(n_out, "null n_out");
     *n_out = 0;
     TVZ_REQUIRE(cap >= 0 && (cap == 0 || (out_video_id && out_count)), "bad output buffers");
@@ -965,6 +974,7 @@ int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q,
     }
     if (out_kth) memcpy(out_kth, ws->h_kth, n_hits * 4);
     return TVZ_OK;
+    });
 }
 
 }  // extern "C"
@@ -1009,6 +1019,7 @@ int tvz_catalog_batch_limit(void) { return kParamKeys; }
 int tvz_catalog_match_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all, const int64_t *q_off,
                             int n_queries, int min_match, int32_t *out_video_id, int32_t *out_count,
                             int64_t *out_off, int64_t cap_total, int64_t *need_per_query, int64_t *need_total_out) {
+    return guarded([&]() -> int {
     TVZ_REQUIRE(cat && ws && ws->cat == cat, "workspace does not belong to this catalogue");
     TVZ_REQUIRE(n_queries >= 0 && q_off && out_off && need_per_query && need_total_out, "bad arguments");
     *need_per_query = 0;
@@ -1110,6 +1121,7 @@ int tvz_catalog_match_batch(const tvz_catalog *cat, tvz_match_ws *ws, const doub
                          "query (workspace holds %lld)", need_total, (long long)cap_total, need_cap, ws->cap);
     }
     return TVZ_OK;
+    });
 }
 
 }  // extern "C"

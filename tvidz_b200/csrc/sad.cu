@@ -86,20 +86,29 @@ __device__ __forceinline__ void load_tile(uint4 (&dst)[kVec], const uint4 *stage
     }
 }
 
-template <int kVec>
+// k16 = false: 8-bit samples (ff_scene_sad_c);  k16 = true: 16-bit samples (ff_scene_sad16_c, the
+// path FFmpeg takes for yuv420p10), two per 32-bit word.
+template <int kVec, bool k16>
 __device__ __forceinline__ unsigned sad_tile(const uint4 (&a)[kVec], const uint4 (&b)[kVec]) {
     unsigned acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;  // four chains: VABSDIFF4.ACC is a dependent add
 #pragma unroll
     for (int j = 0; j < kVec; ++j) {
-        acc0 = __vsadu4(a[j].x, b[j].x) + acc0;
-        acc1 = __vsadu4(a[j].y, b[j].y) + acc1;
-        acc2 = __vsadu4(a[j].z, b[j].z) + acc2;
-        acc3 = __vsadu4(a[j].w, b[j].w) + acc3;
+        if (k16) {
+            acc0 = __vsadu2(a[j].x, b[j].x) + acc0;
+            acc1 = __vsadu2(a[j].y, b[j].y) + acc1;
+            acc2 = __vsadu2(a[j].z, b[j].z) + acc2;
+            acc3 = __vsadu2(a[j].w, b[j].w) + acc3;
+        } else {
+            acc0 = __vsadu4(a[j].x, b[j].x) + acc0;
+            acc1 = __vsadu4(a[j].y, b[j].y) + acc1;
+            acc2 = __vsadu4(a[j].z, b[j].z) + acc2;
+            acc3 = __vsadu4(a[j].w, b[j].w) + acc3;
+        }
     }
-    return (acc0 + acc1) + (acc2 + acc3);  // <= 255 * 16 * kVec per thread
+    return (acc0 + acc1) + (acc2 + acc3);  // <= 255 * 16 * kVec (u8) or 65535 * 8 * kVec (u16) per thread
 }
 
-template <int kStages, int kVec>
+template <int kStages, int kVec, bool k16>
 __global__ void __launch_bounds__(kSadThreads) sad_bulk_kernel(const SadParams p) {
     constexpr int kTileCap = kConsumerThreads * kVec * 16;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -172,13 +181,13 @@ __global__ void __launch_bounds__(kSadThreads) sad_bulk_kernel(const SadParams p
         int f = 1;
         for (; f + 1 < un.nf; f += 2) {
             acquire(rb);
-            publish(sad_tile<kVec>(ra, rb), f);
+            publish(sad_tile<kVec, k16>(ra, rb), f);
             acquire(ra);
-            publish(sad_tile<kVec>(rb, ra), f + 1);
+            publish(sad_tile<kVec, k16>(rb, ra), f + 1);
         }
         if (f < un.nf) {
             acquire(rb);
-            publish(sad_tile<kVec>(ra, rb), f);
+            publish(sad_tile<kVec, k16>(ra, rb), f);
         }
     }
 }
@@ -230,6 +239,36 @@ __global__ void __launch_bounds__(kGenThreads) sad_generic_kernel(const uint8_t 
     }
 }
 
+// 16-bit samples on layouts the bulk kernel cannot take: plain loads, same decomposition.
+__global__ void __launch_bounds__(kGenThreads) sad_generic16_kernel(const uint8_t *__restrict__ base, int n_frames,
+                                                                    int width, int height, long long pitch,
+                                                                    long long frame_stride, long long stream_stride,
+                                                                    unsigned long long *sad, long long sad_stride) {
+    const int t = blockIdx.y + 1;
+    const int s = blockIdx.z;
+    if (t >= n_frames) return;
+    const uint8_t *cur = base + s * stream_stride + t * frame_stride;
+    const uint8_t *prv = cur - frame_stride;
+    const int y0 = blockIdx.x * kGenRows;
+    const int y1 = min(y0 + kGenRows, height);
+    unsigned long long acc = 0;
+    for (int y = y0; y < y1; ++y) {
+        const uint16_t *a = reinterpret_cast<const uint16_t *>(prv + y * pitch);
+        const uint16_t *b = reinterpret_cast<const uint16_t *>(cur + y * pitch);
+        for (int x = threadIdx.x; x < width; x += kGenThreads) acc += abs(int(a[x]) - int(b[x]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ unsigned long long warp_sums[kGenThreads / 32];
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
+        for (int i = 0; i < kGenThreads / 32; ++i) tot += warp_sums[i];
+        atomicAdd(sad + s * sad_stride + t, tot);
+    }
+}
+
 // FFmpeg f_select.c get_scene_score + gt(scene, T): lag-1 dependency only, so every
 // (stream, frame) is independent.  IEEE double division, one float32 rounding.
 __global__ void scene_select_kernel(const unsigned long long *__restrict__ sad, int n_streams, int n_frames,
@@ -270,11 +309,11 @@ constexpr Variant kVariants[] = {{6, 8}, {4, 4}, {3, 8}, {8, 4}, {12, 4}, {4, 8}
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 template <int kStages, int kVec>
-int launch_bulk(const SadParams &p, int ctas_per_sm, cudaStream_t st) {
+int launch_bulk(const SadParams &p, int ctas_per_sm, bool is16, cudaStream_t st) {
     constexpr int kTileCap = kConsumerThreads * kVec * 16;
     constexpr int smem = kStages * kTileCap + 2 * kStages * 8;
     static_assert(smem <= 227 * 1024, "ring does not fit shared memory");
-    auto kern = sad_bulk_kernel<kStages, kVec>;
+    auto kern = is16 ? sad_bulk_kernel<kStages, kVec, true> : sad_bulk_kernel<kStages, kVec, false>;
     TVZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int fit = std::max(1, (227 * 1024) / (smem + 1024));
     if (ctas_per_sm <= 0 || ctas_per_sm > fit) ctas_per_sm = fit;
@@ -296,17 +335,25 @@ bool bulk_eligible(const uint8_t *d_luma, int width, int height, long long pitch
 }  // namespace
 
 // d_sad must already be zero at [s][1..n_frames) (callers memset); accumulates SADs there.
+// `width` is the visible row length in BYTES (= samples for 8-bit, 2 x samples for 16-bit).
 int sad_accumulate(const uint8_t *d_luma, int n_streams, int n_frames, int width, int height, long long pitch,
                    long long frame_stride, long long stream_stride, unsigned long long *d_sad, long long sad_stride,
-                   cudaStream_t st) {
+                   cudaStream_t st, bool is16) {
     if (n_streams <= 0 || n_frames <= 1) return TVZ_OK;
     if (!bulk_eligible(d_luma, width, height, pitch, frame_stride, stream_stride)) {
         dim3 grid((height + kGenRows - 1) / kGenRows, n_frames - 1, n_streams);
         TVZ_REQUIRE(grid.y <= 65535 && grid.z <= 65535,
                     "generic SAD path: n_frames-1 and n_streams must be <= 65535 (got %d, %d)", n_frames - 1,
                     n_streams);
-        sad_generic_kernel<<<grid, kGenThreads, 0, st>>>(d_luma, n_frames, width, height, pitch, frame_stride,
-                                                         stream_stride, d_sad, sad_stride);
+        if (is16) {
+            TVZ_REQUIRE(((reinterpret_cast<uintptr_t>(d_luma) | pitch | frame_stride | stream_stride) & 1) == 0,
+                        "16-bit luma needs 2-byte aligned base, pitch and strides");
+            sad_generic16_kernel<<<grid, kGenThreads, 0, st>>>(d_luma, n_frames, width / 2, height, pitch, frame_stride,
+                                                               stream_stride, d_sad, sad_stride);
+        } else {
+            sad_generic_kernel<<<grid, kGenThreads, 0, st>>>(d_luma, n_frames, width, height, pitch, frame_stride,
+                                                             stream_stride, d_sad, sad_stride);
+        }
         TVZ_CUDA(cudaGetLastError());
         return TVZ_OK;
     }
@@ -354,12 +401,12 @@ int sad_accumulate(const uint8_t *d_luma, int n_streams, int n_frames, int width
     p.n_units = spatial * p.n_segs;
 
     switch (tn.variant) {
-        case 0: return launch_bulk<6, 8>(p, tn.ctas_per_sm, st);
-        case 1: return launch_bulk<4, 4>(p, tn.ctas_per_sm, st);
-        case 2: return launch_bulk<3, 8>(p, tn.ctas_per_sm, st);
-        case 3: return launch_bulk<8, 4>(p, tn.ctas_per_sm, st);
-        case 4: return launch_bulk<12, 4>(p, tn.ctas_per_sm, st);
-        case 5: return launch_bulk<4, 8>(p, tn.ctas_per_sm, st);
+        case 0: return launch_bulk<6, 8>(p, tn.ctas_per_sm, is16, st);
+        case 1: return launch_bulk<4, 4>(p, tn.ctas_per_sm, is16, st);
+        case 2: return launch_bulk<3, 8>(p, tn.ctas_per_sm, is16, st);
+        case 3: return launch_bulk<8, 4>(p, tn.ctas_per_sm, is16, st);
+        case 4: return launch_bulk<12, 4>(p, tn.ctas_per_sm, is16, st);
+        case 5: return launch_bulk<4, 8>(p, tn.ctas_per_sm, is16, st);
     }
     return set_error(TVZ_ERR_INVALID, "bad SAD variant %d", tn.variant);
 }
@@ -402,7 +449,23 @@ int tvz_sad_luma_u8(const uint8_t *d_luma, int n_streams, int n_frames, int widt
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TVZ_CUDA(cudaMemsetAsync(d_sad, 0, sizeof(uint64_t) * static_cast<size_t>(n_streams) * n_frames, st));
     return sad_accumulate(d_luma, n_streams, n_frames, width, height, pitch_bytes, frame_stride_bytes,
-                          stream_stride_bytes, reinterpret_cast<unsigned long long *>(d_sad), n_frames, st);
+                          stream_stride_bytes, reinterpret_cast<unsigned long long *>(d_sad), n_frames, st, false);
+}
+
+int tvz_sad_luma_u16(const uint16_t *d_luma, int n_streams, int n_frames, int width, int height,
+                     int64_t pitch_bytes, int64_t frame_stride_bytes, int64_t stream_stride_bytes, uint64_t *d_sad,
+                     void *stream) {
+    TVZ_REQUIRE(n_streams >= 0 && n_frames >= 0, "negative n_streams/n_frames");
+    if (n_streams == 0 || n_frames == 0) return TVZ_OK;
+    TVZ_REQUIRE(d_luma && d_sad, "null pointer");
+    TVZ_REQUIRE(width > 0 && height > 0 && width < (1 << 29), "bad width/height (got %dx%d)", width, height);
+    TVZ_REQUIRE(pitch_bytes >= 2 * (int64_t)width, "pitch %lld < 2 * width %d", (long long)pitch_bytes, width);
+    TVZ_REQUIRE(frame_stride_bytes >= 0 && stream_stride_bytes >= 0, "negative stride");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TVZ_CUDA(cudaMemsetAsync(d_sad, 0, sizeof(uint64_t) * static_cast<size_t>(n_streams) * n_frames, st));
+    return sad_accumulate(reinterpret_cast<const uint8_t *>(d_luma), n_streams, n_frames, 2 * width, height, pitch_bytes,
+                          frame_stride_bytes, stream_stride_bytes, reinterpret_cast<unsigned long long *>(d_sad),
+                          n_frames, st, true);
 }
 
 int tvz_scene_select(const uint64_t *d_sad, int n_streams, int n_frames, int width, int height, int bitdepth,

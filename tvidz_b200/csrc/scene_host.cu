@@ -13,7 +13,7 @@
 namespace tvz {
 int sad_accumulate(const uint8_t *d_luma, int n_streams, int n_frames, int width, int height, long long pitch,
                    long long frame_stride, long long stream_stride, unsigned long long *d_sad, long long sad_stride,
-                   cudaStream_t st);
+                   cudaStream_t st, bool is16);
 int scene_select_launch(const unsigned long long *d_sad, int n_streams, int n_frames, int width, int height,
                         int bitdepth, double threshold, double *d_score, uint8_t *d_selected, cudaStream_t st);
 
@@ -96,7 +96,9 @@ int run(HostCtx &cx, const uint8_t *h_luma, int S, int F, int W, int H, long lon
     int rc = cx.reserve(static_cast<size_t>(S) * d_sstride, elems);
     if (rc) return rc;
     TVZ_CUDA(cudaMemsetAsync(cx.sad, 0, elems * sizeof(unsigned long long), cx.compute));
-    const size_t frame_span = static_cast<size_t>(H - 1) * pitch + W;  // bytes of one frame that matter
+    const bool is16 = bitdepth > 8;
+    const int Wb = is16 ? 2 * W : W;                                   // visible row bytes
+    const size_t frame_span = static_cast<size_t>(H - 1) * pitch + Wb;  // bytes of one frame that matter
     int chunk = 0;
     for (int t0 = 0; t0 < F; t0 += C, ++chunk) {
         const int b = chunk & 1;
@@ -118,10 +120,10 @@ int run(HostCtx &cx, const uint8_t *h_luma, int S, int F, int W, int H, long lon
         }
         TVZ_CUDA(cudaStreamWaitEvent(cx.compute, cx.copied[b], 0));
         if (chunk == 0)  // frames t0.. in slots 1..n, no predecessor
-            rc = sad_accumulate(cx.buf[b] + fstride, S, n, W, H, pitch, fstride, d_sstride, cx.sad, F, cx.compute);
+            rc = sad_accumulate(cx.buf[b] + fstride, S, n, Wb, H, pitch, fstride, d_sstride, cx.sad, F, cx.compute, is16);
         else  // slot 0 = frame t0-1: local index j <-> global frame t0-1+j
-            rc = sad_accumulate(cx.buf[b], S, n + 1, W, H, pitch, fstride, d_sstride, cx.sad + (t0 - 1), F,
-                                cx.compute);
+            rc = sad_accumulate(cx.buf[b], S, n + 1, Wb, H, pitch, fstride, d_sstride, cx.sad + (t0 - 1), F,
+                                cx.compute, is16);
         if (rc) return rc;
     }
     rc = scene_select_launch(cx.sad, S, F, W, H, bitdepth, threshold, cx.score, cx.sel, cx.compute);
@@ -144,15 +146,17 @@ extern "C" int tvz_scene_score_host(const uint8_t *h_luma, int n_streams, int n_
                                     int64_t pitch_bytes, int64_t frame_stride_bytes, int64_t stream_stride_bytes,
                                     int bitdepth, double threshold, int chunk_frames, uint64_t *h_sad,
                                     double *h_score, uint8_t *h_selected) {
+    return guarded([&]() -> int {
     TVZ_REQUIRE(n_streams >= 0 && n_frames >= 0, "negative n_streams/n_frames");
     if (n_streams == 0 || n_frames == 0) return TVZ_OK;
     TVZ_REQUIRE(h_luma, "null frame pointer");
     TVZ_REQUIRE(width > 0 && height > 0, "width and height must be positive (got %dx%d)", width, height);
-    TVZ_REQUIRE(pitch_bytes >= width, "pitch %lld < width %d", (long long)pitch_bytes, width);
-    TVZ_REQUIRE(frame_stride_bytes >= (int64_t)(height - 1) * pitch_bytes + width, "frames overlap");
+    TVZ_REQUIRE(bitdepth >= 8 && bitdepth <= 16, "bitdepth %d out of range (8..16)", bitdepth);
+    const int64_t row_bytes = bitdepth > 8 ? 2 * (int64_t)width : width;
+    TVZ_REQUIRE(pitch_bytes >= row_bytes, "pitch %lld < row of %lld bytes", (long long)pitch_bytes, (long long)row_bytes);
+    TVZ_REQUIRE(frame_stride_bytes >= (int64_t)(height - 1) * pitch_bytes + row_bytes, "frames overlap");
     TVZ_REQUIRE(n_streams == 1 || stream_stride_bytes >= frame_stride_bytes * (int64_t)(n_frames - 1),
                 "streams overlap");
-    TVZ_REQUIRE(bitdepth == 8, "only 8-bit luma is implemented (got %d)", bitdepth);
     int C = chunk_frames;
     if (C <= 0) {
         const long long per_frame = static_cast<long long>(n_streams) * frame_stride_bytes;
@@ -172,4 +176,5 @@ extern "C" int tvz_scene_score_host(const uint8_t *h_luma, int n_streams, int n_
     if (rc) cudaStreamSynchronize(cx->compute), cudaStreamSynchronize(cx->copy);
     checkin(cx);
     return rc;
+    });
 }

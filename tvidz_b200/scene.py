@@ -35,8 +35,8 @@ def _as_4d(frames: torch.Tensor) -> torch.Tensor:
         frames = frames.unsqueeze(0)
     if frames.dim() != 4:
         raise ValueError("frames must be [streams, frames, height, pitch] or [frames, height, pitch]")
-    if frames.dtype != torch.uint8:
-        raise TypeError("frames must be 8-bit luma (torch.uint8)")
+    if frames.dtype not in (torch.uint8, torch.uint16, torch.int16):
+        raise TypeError("frames must be 8-bit luma (torch.uint8) or 16-bit samples (torch.uint16 / int16 bits)")
     return frames
 
 
@@ -44,10 +44,11 @@ def _strides(frames: torch.Tensor):
     S, F, H, P = frames.shape
     ss, fs, ps, es = frames.stride()
     if es != 1 and P > 1:
-        raise ValueError("luma rows must be contiguous bytes")
+        raise ValueError("luma rows must be contiguous samples")
     if S == 1:
         ss = max(ss, fs * F)
-    return int(ps), int(fs), int(ss)
+    b = frames.element_size()                     # strides in BYTES
+    return int(ps) * b, int(fs) * b, int(ss) * b
 
 
 def sad_luma(frames: torch.Tensor, width: int | None = None, stream=None) -> torch.Tensor:
@@ -63,9 +64,9 @@ def sad_luma(frames: torch.Tensor, width: int | None = None, stream=None) -> tor
     W = P if width is None else int(width)
     pitch, fstride, sstride = _strides(frames)
     out = torch.empty((S, F), dtype=torch.int64, device=frames.device)
+    fn = lib().tvz_sad_luma_u8 if frames.element_size() == 1 else lib().tvz_sad_luma_u16
     with torch.cuda.device(frames.device):
-        check(lib().tvz_sad_luma_u8(frames.data_ptr(), S, F, W, H, pitch, fstride, sstride,
-                                    out.data_ptr(), _stream_ptr(stream)))
+        check(fn(frames.data_ptr(), S, F, W, H, pitch, fstride, sstride, out.data_ptr(), _stream_ptr(stream)))
     return out
 
 
@@ -85,47 +86,59 @@ def scene_select(sad: torch.Tensor, width: int, height: int, threshold: float = 
 
 
 def score_frames(frames: torch.Tensor, width: int | None = None, threshold: float = DEFAULT_THRESHOLD,
-                 stream=None):
-    """Device-resident frames -> (sad, score, selected) device tensors [S, F]."""
+                 stream=None, bitdepth: int | None = None):
+    """Device-resident frames -> (sad, score, selected) device tensors [S, F].  16-bit sample tensors
+    (yuv420p10 and deeper) need `bitdepth` (default 10), which scales mafd as f_select.c does."""
     frames = _as_4d(frames)
     S, F, H, P = frames.shape
     W = P if width is None else int(width)
+    if bitdepth is None:
+        bitdepth = 8 if frames.element_size() == 1 else 10
+    if (bitdepth == 8) != (frames.element_size() == 1):
+        raise ValueError("bitdepth 8 goes with uint8 frames, 9..16 with 16-bit frames")
     sad = sad_luma(frames, W, stream)
-    score, sel = scene_select(sad, W, H, threshold, 8, stream)
+    score, sel = scene_select(sad, W, H, threshold, bitdepth, stream)
     return sad, score, sel
 
 
 def score_frames_host(frames, width: int | None = None, threshold: float = DEFAULT_THRESHOLD,
-                      chunk_frames: int = 0, device: int | None = None):
+                      chunk_frames: int = 0, device: int | None = None, bitdepth: int | None = None):
     """Host frames (numpy uint8 or CPU torch tensor [S,F,H,P], ideally pinned) -> numpy
     (sad u64, score f64, selected u8), each [S, F].  Copies host->device inside the call
     (tvz_scene_score_host): this is the end-to-end entry a binding in analyze_file uses."""
     if isinstance(frames, np.ndarray):
-        if frames.dtype != np.uint8:
-            raise TypeError("frames must be uint8")
+        if frames.dtype not in (np.uint8, np.uint16):
+            raise TypeError("frames must be uint8 or uint16")
         if frames.ndim == 3:
             frames = frames[None]
         S, F, H, P = frames.shape
-        ss, fs, ps, es = frames.strides
+        esize = frames.dtype.itemsize
+        ss, fs, ps, es = (x // esize for x in frames.strides)
         ptr = frames.ctypes.data
     else:
         frames = _as_4d(frames)
         if frames.is_cuda:
             raise ValueError("score_frames_host takes host memory")
         S, F, H, P = frames.shape
+        esize = frames.element_size()
         ss, fs, ps, es = frames.stride()
         ptr = frames.data_ptr()
     if es != 1 and P > 1:
-        raise ValueError("luma rows must be contiguous bytes")
+        raise ValueError("luma rows must be contiguous samples")
     if S == 1:
         ss = max(ss, fs * F)
+    if bitdepth is None:
+        bitdepth = 8 if esize == 1 else 10
+    if (bitdepth == 8) != (esize == 1):
+        raise ValueError("bitdepth 8 goes with uint8 frames, 9..16 with 16-bit frames")
+    ss, fs, ps = ss * esize, fs * esize, ps * esize           # the C ABI takes byte strides
     W = P if width is None else int(width)
     sad = np.zeros((S, F), np.uint64)
     score = np.zeros((S, F), np.float64)
     sel = np.zeros((S, F), np.uint8)
     ctx = torch.cuda.device(device) if device is not None else torch.cuda.device(torch.cuda.current_device())
     with ctx:
-        check(lib().tvz_scene_score_host(ptr, S, F, W, H, int(ps), int(fs), int(ss), 8, float(threshold),
+        check(lib().tvz_scene_score_host(ptr, S, F, W, H, int(ps), int(fs), int(ss), int(bitdepth), float(threshold),
                                          int(chunk_frames), sad.ctypes.data, score.ctypes.data, sel.ctypes.data))
     return sad, score, sel
 
