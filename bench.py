@@ -420,6 +420,28 @@ def run_ours(args):
                                          + (" + all_gather)" if world > 1 else ")"),
                                  "peak_source": peak_src},
                     "gpu_launches_per_query": 3}
+        if world > 1 and not args.no_weak:
+            # weak-scaling companion: 1M rows PER GPU (rank r holds rows r*1M.. of a world*1M-row catalogue)
+            wts, woff, wvid = synth.synth_catalogue(CATALOGUE_ROWS, seed=1000 + rank)
+            wvid = (wvid.astype(np.int64) + rank * CATALOGUE_ROWS).astype(np.int32)
+            wsc = ShardedCatalogue(wts, woff, wvid, hit_capacity=1 << 15, device=local, gather=args.gather,
+                                   presharded=True)
+            for _ in range(Wm):
+                wsc.enqueue(q, mm)
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            w0.record(stream)
+            for _ in range(Km):
+                wsc.enqueue(q, mm)
+            w1.record(stream)
+            barrier()
+            w_ms = max_over_ranks(w0.elapsed_time(w1)) / Km
+            w_hits = len(wsc.find_duplicates(q, mm))
+            matching["weak_scaling"] = {"rows": CATALOGUE_ROWS * world, "rows_per_gpu": CATALOGUE_ROWS,
+                                        "value": CATALOGUE_ROWS * world / (w_ms * 1e-3), "unit": "pairs/s",
+                                        "ms_per_query": w_ms, "hits": w_hits, "scaling": "weak",
+                                        "note": "same query against a catalogue of 1M rows per GPU"}
+            del wsc
         if world == 1:
             # 64 concurrent analyses (one per stream of configs[1]) asking at once: 8 queries per catalogue pass
             rng = np.random.default_rng(7)
@@ -554,6 +576,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fragment", action="store_true")
     ap.add_argument("--no-longform", action="store_true")
+    ap.add_argument("--no-weak", action="store_true")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="how the sharded matcher exchanges per-shard hit records at N > 1")
     args = ap.parse_args()

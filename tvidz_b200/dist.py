@@ -65,13 +65,26 @@ class ShardedCatalogue:
     """
 
     def __init__(self, ts, off, video_id, hit_capacity: int = 1 << 15, device=None,
-                 local_factory: Callable | None = None, group=None, gather: str = "nccl"):
+                 local_factory: Callable | None = None, group=None, gather: str = "nccl", presharded: bool = False):
+        """`presharded=True`: (ts, off, video_id) already ARE this rank's shard (catalogues too large to
+        materialise on every rank); shards concatenate in rank order."""
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        self.bounds = shard_bounds(off, self.world)
-        lo, hi = self.bounds[self.rank]
-        s_ts, s_off, s_vid = take_shard(np.asarray(ts), np.asarray(off), np.asarray(video_id), lo, hi)
+        if presharded:
+            n_local = torch.tensor([len(video_id)], dtype=torch.int64,
+                                   device="cpu" if local_factory is not None else torch.device("cuda", device if device is not None else torch.cuda.current_device()))
+            sizes = [torch.zeros_like(n_local) for _ in range(self.world)]
+            dist.all_gather(sizes, n_local, group=group)
+            edges = np.concatenate([[0], np.cumsum([int(x.item()) for x in sizes])])
+            self.bounds = [(int(edges[r]), int(edges[r + 1])) for r in range(self.world)]
+            lo, hi = self.bounds[self.rank]
+            s_ts, s_off, s_vid = (np.ascontiguousarray(ts, np.float64), np.ascontiguousarray(off, np.int64),
+                                  np.ascontiguousarray(video_id, np.int32))
+        else:
+            self.bounds = shard_bounds(off, self.world)
+            lo, hi = self.bounds[self.rank]
+            s_ts, s_off, s_vid = take_shard(np.asarray(ts), np.asarray(off), np.asarray(video_id), lo, hi)
         if local_factory is None:
             from .catalog import Catalogue
             dev = torch.cuda.current_device() if device is None else device
