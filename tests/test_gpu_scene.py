@@ -256,3 +256,37 @@ def test_ten_bit_luma(cuda, S, F, H, W, P):
     k[0, 1] = 1023
     sad, score, sel = scene.score_frames(torch.from_numpy(k.view(np.int16)).to(cuda), bitdepth=10)
     assert sad.tolist() == [[0, 1023 * 128]] and score.tolist() == [[0.0, 1.0]]
+
+
+def test_concurrent_analyses_like_the_reference(cuda):
+    """The reference runs analyze_file on one thread per upload (app.py:43,472): several threads go
+    through the host-buffer entry and the Inspector at once and must get what a serial run gets."""
+    import threading
+    from tvidz_b200.inspector import Inspector
+    clips = [synth.synth_frames(1, 90, 270, 480, seed=200 + i, scene_len=(6, 15))[0] for i in range(6)]
+    want = []
+    for c in clips:
+        _, _, o_sel, _ = oracle.scene_batch(c[None].numpy())
+        want.append(oracle.cut_timestamps(o_sel[0]))
+    ins = Inspector()
+    for i in (0, 3):                                   # two of the clips were uploaded before
+        v = ins.add_video("old-%d.mp4" % i)
+        ins.add_timestamps(v.id, want[i])
+    results = [None] * len(clips)
+
+    def work(i):
+        for _ in range(3):
+            sad, score, sel = scene.score_frames_host(clips[i].numpy(), chunk_frames=16)
+            assert scene.cut_timestamps(sel[0]) == want[i]
+        results[i] = ins.analyze_frames("up-%d.mp4" % i, clips[i].numpy())
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(clips))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i, r in enumerate(results):
+        assert r is not None and r["status"] == "done", (i, r)
+        if i in (0, 3):
+            assert r["duplicates"] == ["old-%d.mp4" % i] and r["scene_cuts"] == want[i][:2]
+        else:
+            assert r["scene_cuts"] == want[i] or r["duplicates"]      # may match an earlier concurrent upload only by chance
+            assert r["total_cuts"] == len(r["scene_cuts"])
