@@ -172,7 +172,9 @@ const int32_t *tvz_match_ws_counts(const tvz_match_ws *ws);  /* int32 [rows] scr
  * implements only offset-0 exact membership (inspector/db.py:78-79), so the
  * semantics are this library's own (tvidz_b200/csrc/fragment.cu header):
  *   ticks = llround(ts * tick_hz); candidate offsets d = C[j] - Q[i] come from
- *   adjacent cut pairs whose intervals agree within tol_gap ticks;
+ *   positions where `anchor_intervals` (1..3) consecutive intervals of row and query agree
+ *   within tol_gap ticks (1 = any agreeing adjacent pair; 2 = two in a row, far fewer candidates:
+ *   the catalogue is then streamed once at HBM speed);
  *   score(d) = #{i : some C[j] within tol ticks of Q[i] + d}; a row reports its
  *   best (score, d) -- ties: smaller |d|, then smaller d -- iff score >= min_match.
  *   zero_offset_only = 1 scores d = 0 alone; with tol 0 that is find_duplicates'
@@ -188,14 +190,15 @@ int64_t tvz_fragcat_values(const tvz_fragcat *cat);   /* stored ticks (4 bytes e
 
 /* Host-buffer call: results (catalogue order) in host arrays of `cap` entries. */
 int tvz_fragcat_match(tvz_fragcat *cat, const double *q, int qn, int min_match, int tol_ticks, int tol_gap_ticks,
-                      int zero_offset_only, int32_t *out_video_id, int32_t *out_score, int32_t *out_delta_ticks,
+                      int anchor_intervals, int zero_offset_only, int32_t *out_video_id, int32_t *out_score, int32_t *out_delta_ticks,
                       int64_t cap, int64_t *n_out);
 
 /* Device-resident variant: d_out is int32 [3 * (out_cap + 1)] on the device:
  *   d_out[0..1] = { n_hits saturated, overflow flag }, d_out[2 + 2h ..] = { video_id, score },
  *   d_out[2 * (out_cap + 1) + 1 + h] = offset ticks of hit h.  One fixed-size record per shard. */
 int tvz_fragcat_match_async(tvz_fragcat *cat, const double *h_q, int qn, int min_match, int tol_ticks,
-                            int tol_gap_ticks, int zero_offset_only, int32_t *d_out, int64_t out_cap, void *stream);
+                            int tol_gap_ticks, int anchor_intervals, int zero_offset_only, int32_t *d_out,
+                            int64_t out_cap, void *stream);
 
 #ifdef __cplusplus
 }

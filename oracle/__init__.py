@@ -93,7 +93,7 @@ def lib() -> ctypes.CDLL:
                                      c.c_void_p, c.c_int]
         L.tvzo_fragment_rows.restype = None
         L.tvzo_fragment_rows.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_void_p, c.c_int, c.c_double, c.c_int,
-                                         c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_int]
+                                         c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_int]
         _lib = L
     return _lib
 
@@ -180,8 +180,8 @@ def find_duplicates_csr(ts, off, video_id, q, min_match=5, n_threads: int = 0):
 
 
 # ---------------------------------------------------------------- fragment mode (builder-defined spec)
-def fragment_rows(ts, off, q, tick_hz: float = 1000.0, tol: int = 7, tol_gap: int = 14, zero_only: bool = False,
-                  n_threads: int = 0):
+def fragment_rows(ts, off, q, tick_hz: float = 1000.0, tol: int = 7, tol_gap: int = 14, anchor: int = 2,
+                  zero_only: bool = False, n_threads: int = 0):
     """Best (score, offset ticks) per row under the interval-anchored spec -> (int32 [N], int64 [N])."""
     ts = np.ascontiguousarray(ts, np.float64)
     off = np.ascontiguousarray(off, np.int64)
@@ -189,7 +189,7 @@ def fragment_rows(ts, off, q, tick_hz: float = 1000.0, tol: int = 7, tol_gap: in
     n = off.shape[0] - 1
     score = np.zeros(n, np.int32)
     delta = np.zeros(n, np.int64)
-    lib().tvzo_fragment_rows(_p(ts), _p(off), n, _p(q), q.shape[0], tick_hz, tol, tol_gap, int(zero_only),
+    lib().tvzo_fragment_rows(_p(ts), _p(off), n, _p(q), q.shape[0], tick_hz, tol, tol_gap, int(anchor), int(zero_only),
                              _p(score), _p(delta), n_threads)
     return score, delta
 

@@ -67,7 +67,7 @@ static int better(int s, int64_t d, int bs, int64_t bd)
 
 /* For every row: best score and its offset (ticks).  score_out/delta_out: [n_rows]. */
 void tvzo_fragment_rows(const double *ts, const int64_t *off, int64_t n_rows, const double *q, int qn,
-                        double tick_hz, int tol, int tol_gap, int zero_only,
+                        double tick_hz, int tol, int tol_gap, int anchor, int zero_only,
                         int32_t *score_out, int64_t *delta_out, int n_threads)
 {
     int64_t *Q = (int64_t *)malloc(sizeof(int64_t) * (size_t)(qn > 0 ? qn : 1));
@@ -86,10 +86,15 @@ void tvzo_fragment_rows(const double *ts, const int64_t *off, int64_t n_rows, co
             if (zero_only) {
                 bs = score_offset(C, L, Q, nq, 0, tol);
             } else {
-                for (int i = 0; i + 1 < nq; i++)
-                    for (int j = 0; j + 1 < L; j++) {
-                        int64_t diff = (C[j + 1] - C[j]) - (Q[i + 1] - Q[i]);
-                        if (diff > tol_gap || diff < -tol_gap) continue;
+                /* candidates: `anchor` consecutive intervals of query and row agree within tol_gap */
+                for (int i = 0; i + anchor < nq; i++)
+                    for (int j = 0; j + anchor < L; j++) {
+                        int agree = 1;
+                        for (int a = 0; a < anchor && agree; a++) {
+                            int64_t diff = (C[j + a + 1] - C[j + a]) - (Q[i + a + 1] - Q[i + a]);
+                            if (diff > tol_gap || diff < -tol_gap) agree = 0;
+                        }
+                        if (!agree) continue;
                         int64_t d = C[j] - Q[i];
                         int s = score_offset(C, L, Q, nq, d, tol);
                         if (better(s, d, bs, bd)) { bs = s; bd = d; }

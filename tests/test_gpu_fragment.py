@@ -35,16 +35,46 @@ def test_clip_is_found_at_its_offset(cuda):
     cat.close()
 
 
+@pytest.mark.parametrize("anchor", [1, 2, 3])
 @pytest.mark.parametrize("min_match", [2, 3, 5])
-def test_matches_oracle_all_rows(cuda, min_match):
+def test_matches_oracle_all_rows(cuda, min_match, anchor):
     ts, off, vid = _long_catalogue(1500, seed=5)
     cat = FragmentCatalogue(ts, off, vid, hit_capacity=8)          # forces the capacity regrowth path
     row = ts[off[77]:off[78]]
     q = clip_query(row, 12_345)
-    v, s, d = cat.match(q, min_match)
-    want = oracle.find_fragments_csr(ts, off, vid, q, min_match=min_match)
+    v, s, d = cat.match(q, min_match, anchor=anchor)
+    want = oracle.find_fragments_csr(ts, off, vid, q, min_match=min_match, anchor=anchor)
     assert list(zip(v.tolist(), s.tolist(), d.tolist())) == want
-    assert len(want) > 1 or min_match == 5
+    assert len(want) > 1 or min_match == 5 or anchor > 1
+    assert (int(vid[77]), len(q)) in list(zip(v.tolist(), s.tolist()))
+    cat.close()
+
+
+@pytest.mark.parametrize("anchor", [2, 3])
+def test_streaming_kernel_ragged_rows_and_long_queries(cuda, anchor):
+    """The streaming kernel reads the shard as one flat array: rows of every length (empty, shorter
+    than an anchor, straddling warp / CTA chunk boundaries), intervals beyond the bucket range, dense
+    true matches (every row is a shifted copy) and queries with more than 32 intervals (the
+    bucket sets are indexed mod 32)."""
+    rng = np.random.default_rng(40 + anchor)
+    base = np.cumsum(rng.integers(15, 150, 6000)) / 30.0
+    base[3000:] += 40.0                                            # one interval of > 32767 ticks
+    rows = []
+    for i in range(900):
+        n = int(rng.choice([0, 1, 2, 3, 4, 7, 60, 300, 1100]))
+        a = int(rng.integers(0, 6000 - n))
+        shift = float(rng.integers(0, 100)) if i % 3 else 0.0
+        rows.append((i + 1, (np.round((base[a:a + n] + shift) * 1000) / 1000).tolist()))
+    from tvidz_b200.catalog import rows_to_csr
+    ts, off, vid = rows_to_csr(rows)
+    assert off[-1] > 6 * 8192                                     # several CTA chunks
+    cat = FragmentCatalogue(ts, off, vid, hit_capacity=64)
+    for a, n, mm in ((100, 8, 3), (2990, 20, 5), (500, 50, 4), (1234, 90, 0)):
+        q = (np.round(base[a:a + n] * 1000) / 1000).tolist()
+        v, s, d = cat.match(q, mm, anchor=anchor)
+        want = oracle.find_fragments_csr(ts, off, vid, q, min_match=mm, anchor=anchor)
+        assert list(zip(v.tolist(), s.tolist(), d.tolist())) == want, (a, n, mm)
+        assert len(want) > 3
     cat.close()
 
 
@@ -58,9 +88,11 @@ def test_short_rows_tolerances_and_edges(cuda):
     q = [0.5, 1.0, 2.5, 4.0]
     for tol, tol_gap in ((0, 0), (2, 4), (7, 14)):
         for mm in (0, 1, 2, 4):
-            v, s, d = cat.match(q, mm, tol=tol, tol_gap=tol_gap)
-            assert list(zip(v.tolist(), s.tolist(), d.tolist())) == \
-                oracle.find_fragments_csr(ts, off, vid, q, min_match=mm, tol=tol, tol_gap=tol_gap), (tol, mm)
+            for anchor in (1, 2, 3):
+                v, s, d = cat.match(q, mm, tol=tol, tol_gap=tol_gap, anchor=anchor)
+                assert list(zip(v.tolist(), s.tolist(), d.tolist())) == \
+                    oracle.find_fragments_csr(ts, off, vid, q, min_match=mm, tol=tol, tol_gap=tol_gap,
+                                              anchor=anchor), (tol, mm, anchor)
     res = dict((v, (s, o)) for v, s, o in cat.find_fragments(q, 4))
     assert res[1] == (4, 0.0) and res[2] == (4, 100.0) and res[6] == (4, 0.0) and res[7][0] == 4
     assert 7 not in dict((v, s) for v, s, _ in cat.find_fragments(q, 4, tol=0, tol_gap=0))
@@ -94,9 +126,11 @@ def test_long_rows_read_in_place(cuda):
     cat = FragmentCatalogue(ts, off, vid)
     row = ts[off[5]:off[6]]
     q = clip_query(row, 30_000, n_frames=1800)
-    v, s, d = cat.match(q, 3)
-    assert list(zip(v.tolist(), s.tolist(), d.tolist())) == oracle.find_fragments_csr(ts, off, vid, q, min_match=3)
-    assert (int(vid[5]), len(q)) in list(zip(v.tolist(), s.tolist()))
+    for anchor in (1, 2):
+        v, s, d = cat.match(q, 3, anchor=anchor)
+        assert list(zip(v.tolist(), s.tolist(), d.tolist())) == \
+            oracle.find_fragments_csr(ts, off, vid, q, min_match=3, anchor=anchor)
+        assert (int(vid[5]), len(q)) in list(zip(v.tolist(), s.tolist()))
     cat.close()
 
 
@@ -111,11 +145,13 @@ def test_full_size_config5(cuda):
     f0 = 40_000
     q = clip_query(row, f0)
     assert len(q) >= 6
-    got = cat.find_fragments(q, min_match=5)
-    top = cat.find_fragments(q, min_match=5, top_k=1)[0]
-    assert top[0] == int(vid[r]) and top[1] == len(q) and abs(top[2] - f0 / 30.0) <= 0.008
-    lo, hi = r - 1500, r + 1500
-    sub = oracle.find_fragments_csr(ts[off[lo]:off[hi]], off[lo:hi + 1] - off[lo], vid[lo:hi], q, min_match=5)
-    ids = set(vid[lo:hi].tolist())
-    assert [(v, s, round(o * 1000)) for v, s, o in got if v in ids] == sub
+    for anchor in (2, 1):
+        got = cat.find_fragments(q, min_match=5, anchor=anchor)
+        top = cat.find_fragments(q, min_match=5, top_k=1, anchor=anchor)[0]
+        assert top[0] == int(vid[r]) and top[1] == len(q) and abs(top[2] - f0 / 30.0) <= 0.008
+        lo, hi = r - 1500, r + 1500
+        sub = oracle.find_fragments_csr(ts[off[lo]:off[hi]], off[lo:hi + 1] - off[lo], vid[lo:hi], q, min_match=5,
+                                        anchor=anchor)
+        ids = set(vid[lo:hi].tolist())
+        assert [(v, s, round(o * 1000)) for v, s, o in got if v in ids] == sub
     cat.close()

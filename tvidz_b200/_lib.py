@@ -38,8 +38,8 @@ SYMBOLS = [
     ("tvz_fragcat_destroy", None, [_vp]),
     ("tvz_fragcat_rows", _i64, [_vp]),
     ("tvz_fragcat_values", _i64, [_vp]),
-    ("tvz_fragcat_match", _i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
-    ("tvz_fragcat_match_async", _i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
+    ("tvz_fragcat_match", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
+    ("tvz_fragcat_match_async", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
 ]
 # debug hooks outside the public header
 _DEBUG_SYMBOLS = [("tvz_debug_sad_tuning", _i, [_i, _i, _i, _i]),

@@ -36,10 +36,28 @@ int compact_blocks(long long n_rows);
 int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid, int *out, long long *rows_out,
                     long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket,
                     const int *aux, int *aux_out, cudaStream_t st, const GatherTargets *gather = nullptr);
+int compact_enqueue_keys(unsigned long long *keys, long long n_rows, int min_match, const int *vid, int *out,
+                         long long *rows_out, long long cap, long long *n_hits_out, unsigned long long *state,
+                         unsigned *ticket, int *delta_out, cudaStream_t st);
 int gather_wait_enqueue(const unsigned *d_flags, int n_peers, unsigned epoch, cudaStream_t st);
 int compact_enqueue_batch(int *counts, long long n_rows, int min_match, const int *vid, int *out, long long *rows_out,
                           long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket, int n_batch,
                           const BatchStrides &bs, cudaStream_t st);
+
+// Fragment mode: a row's best candidate as ONE u64 so that concurrent warps can combine theirs with
+// atomicMax.  Order = the spec's: higher score, then smaller |d|, then smaller d.  |d| < 2^30.
+__host__ __device__ __forceinline__ unsigned long long frag_key(int score, int d) {
+    const unsigned ad = static_cast<unsigned>(d < 0 ? -d : d);
+    return (static_cast<unsigned long long>(static_cast<unsigned>(score)) << 32) |
+           (0xffffffffu - (2u * ad + (d > 0 ? 1u : 0u)));
+}
+__host__ __device__ __forceinline__ int frag_key_score(unsigned long long k) { return static_cast<int>(k >> 32); }
+__host__ __device__ __forceinline__ int frag_key_delta(unsigned long long k) {
+    if (k == 0) return 0;  // no candidate: (score 0, offset 0)
+    const unsigned x = 0xffffffffu - static_cast<unsigned>(k);
+    const int ad = static_cast<int>(x >> 1);
+    return (x & 1u) ? ad : -ad;
+}
 
 }  // namespace tvz
 #include <exception>

@@ -6,8 +6,10 @@
 //
 // Spec ("interval-anchored alignment"), on integer ticks t = llround(ts * tick_hz):
 //   * rows and the query are sets of ticks, sorted ascending, duplicates removed;
-//   * a candidate offset d = C[j] - Q[i] is generated by every pair of ADJACENT cuts whose
-//     intervals agree:  | (C[j+1]-C[j]) - (Q[i+1]-Q[i]) | <= tol_gap;
+//   * a candidate offset d = C[j] - Q[i] is generated wherever `anchor` CONSECUTIVE intervals
+//     agree:  | (C[j+a+1]-C[j+a]) - (Q[i+a+1]-Q[i+a]) | <= tol_gap  for a = 0 .. anchor-1
+//     (anchor = 1: every agreeing pair of adjacent cuts, the most permissive; anchor = 2, the
+//     default of the Python API: two agreeing intervals in a row, i.e. three cuts);
 //   * score(d) = #{ i : exists j with | Q[i] + d - C[j] | <= tol };
 //   * the row's verdict is the candidate with the highest score (ties: smaller |d|, then
 //     smaller d); the row is reported iff that score >= min_match, as
@@ -15,7 +17,10 @@
 //   * zero_offset_only = 1 replaces the candidate set by {0}: with tol = 0 the score is
 //     then the reference's match_count (db.py:85-89) on tick-exact data.
 //
-// Kernel: one warp per row.  The row's int32 ticks are staged into a per-warp shared-memory
+// Two kernels.  anchor >= 2 (fragment_stream_kernel, below): agreeing interval n-grams are rare, so
+// the whole catalogue is STREAMED as one flat int32 array -- 256-bit loads, one bucket-table lookup
+// per stored tick, rows resolved only for the few survivors -- and the kernel is HBM-bound.
+// anchor = 1 / zero_offset_only (fragment_match_kernel): one warp per row.  The row's int32 ticks are staged into a per-warp shared-memory
 // buffer with coalesced loads (4 B per stored timestamp is all the HBM traffic).  Every row
 // interval is tested against a 4 KB bitmap of the (tolerance-widened) query intervals; the
 // ~10% that survive look up their matching query intervals in the sorted interval list, the
@@ -246,6 +251,232 @@ fragment_match_kernel(const int *__restrict__ ticks, const long long *__restrict
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// anchor >= 2: streaming kernel.
+//
+// The tick array of the whole shard is read ONCE, front to back, regardless of row boundaries
+// (4 B per stored timestamp; `off` is touched only for survivors).  A warp owns 1024 consecutive
+// ticks per iteration as four 256-bit loads per lane (rolling prefetch: a unit's registers are
+// reloaded from the next chunk as soon as it has been tested).  Per tick: the interval to the next
+// tick indexes a 2048-entry shared-memory table whose entry is a 32-bit set of the query intervals
+// (index mod 32) that could agree with an interval in that bucket; position p survives iff some
+// query interval i is in the set of p, i+1 in the set of p+1 (, i+2 in the set of p+2):
+//     hit(p) = m[p] & rotr(m[p+1], 1) [& rotr(m[p+2], 2)]
+// -- a rotate and an AND per tick, one REDUX.OR per 256 ticks.  Intervals that straddle two rows
+// are garbage and are rejected with everything else when a survivor is resolved: row through the
+// coarse index + a short search in `off`, exact interval test against every query position the
+// set names, then the same anchored merge walk as the per-row kernel scores the offset and the
+// row's best candidate is combined across warps with one 64-bit atomicMax (frag_key).
+constexpr int kStreamThreads = 256;
+constexpr int kStreamWarps = kStreamThreads / 32;
+constexpr int kStreamUnits = 4;                          // 256-bit loads in flight per thread
+constexpr int kUnitTicks = 32 * 8;                       // one warp-wide 256-bit load
+constexpr int kWarpChunk = kStreamUnits * kUnitTicks;    // 1024 consecutive ticks per warp per iteration
+constexpr int kCtaChunk = kStreamWarps * kWarpChunk;     // 8192 ticks = 32 KB
+constexpr int kStreamQueue = 64;                         // survivors parked per warp
+constexpr int kStreamBlockShift = 8;                     // coarse row index: one entry per 256 ticks
+constexpr int kMaxAnchor = 3;
+constexpr int kPadTick = 0x7fffffff;
+
+struct StreamSmem {
+    unsigned table[kMaxBuckets];                    // bucket -> set of query intervals (index mod 32)
+    int q[kFragMaxQ];
+    long long qpos[kStreamWarps][kStreamQueue];
+    unsigned qset[kStreamWarps][kStreamQueue];
+};
+
+struct I32x8 {
+    int t[8];
+};
+__device__ __forceinline__ I32x8 ld_stream_ticks(const int *p) {  // LDG.E.256, no L1 allocation, evict-first in L2
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
+                 : "l"(p));
+    I32x8 r;
+    r.t[0] = static_cast<int>(a); r.t[1] = static_cast<int>(a >> 32);
+    r.t[2] = static_cast<int>(b); r.t[3] = static_cast<int>(b >> 32);
+    r.t[4] = static_cast<int>(c); r.t[5] = static_cast<int>(c >> 32);
+    r.t[6] = static_cast<int>(d); r.t[7] = static_cast<int>(d >> 32);
+    return r;
+}
+__device__ __forceinline__ unsigned rotr32(unsigned x, int n) { return __funnelshift_r(x, x, n); }
+
+// Everything a survivor needs to be parked and resolved; lives in local memory and is touched only
+// on the rare path.
+struct StreamCtx {
+    const int *ticks;
+    const long long *off;
+    const int *block_row;
+    unsigned long long *keys;
+    const int *q;          // shared memory
+    long long *qpos;       // this warp's queue (shared memory)
+    unsigned *qset;
+    long long n_vals;
+    int qn, tol, tol_gap, min_match;
+    int queued;            // warp-uniform, <= kStreamQueue
+};
+struct StreamSets {
+    unsigned m[8 + kMaxAnchor - 1];
+};
+
+// Survivor at flat position `pos` whose set names the query intervals (mod 32) that may start an
+// agreeing run of A intervals there: find its row, test exactly, score, combine into keys[row].
+template <int A>
+__device__ __forceinline__ void stream_resolve(const StreamCtx &cx, long long pos, unsigned set) {
+    if (pos + A >= cx.n_vals) return;  // padding
+    const long long b = pos >> kStreamBlockShift;
+    long long a = cx.block_row[b], z = cx.block_row[b + 1] + 1;  // last row with off[row] <= pos is in [a, z)
+    while (z - a > 1) {
+        const long long mid = (a + z) >> 1;
+        if (cx.off[mid] <= pos) a = mid; else z = mid;
+    }
+    const long long rb = cx.off[a], re = cx.off[a + 1];
+    if (pos + A >= re) return;          // the anchor's A + 1 cuts must all belong to this row
+    const int *C = cx.ticks + rb;
+    const int L = static_cast<int>(re - rb), j = static_cast<int>(pos - rb);
+    int cg[A];
+#pragma unroll
+    for (int k = 0; k < A; ++k) cg[k] = __ldg(C + j + k + 1) - __ldg(C + j + k);
+    const int c0 = __ldg(C + j);
+    unsigned long long best = 0;
+    while (set) {
+        const int bit = __ffs(set) - 1;
+        set &= set - 1;
+        for (int i = bit; i + A < cx.qn; i += 32) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+                const int diff = cg[k] - (cx.q[i + k + 1] - cx.q[i + k]);
+                ok = ok && diff <= cx.tol_gap && diff >= -cx.tol_gap;
+            }
+            if (!ok) continue;
+            const int d = c0 - cx.q[i];
+            const int s = score_anchored(C, L, cx.q, cx.qn, d, cx.tol, i, j, cx.min_match);
+            if (s >= cx.min_match) best = max(best, frag_key(s, d));
+        }
+    }
+    if (best) atomicMax(&cx.keys[a], best);
+}
+
+// Resolve the warp's parked survivors, 32 at a time (called by the whole warp).
+template <int A>
+__device__ __noinline__ void stream_drain(StreamCtx &cx) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    for (int i = lane; i < cx.queued; i += 32) stream_resolve<A>(cx, cx.qpos[i], cx.qset[i]);
+    __syncwarp();
+    cx.queued = 0;
+}
+
+// A unit (8 consecutive ticks per lane) in which some lane has a surviving position: park them.
+// Slots come from the vote mask (no atomics); the queue is drained first whenever a full warp's
+// worth might not fit.
+template <int A>
+__device__ __noinline__ void stream_park_unit(StreamCtx &cx, const StreamSets &ss, unsigned any, long long pos) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (!(any & (1u << k))) continue;
+        unsigned set = ss.m[k];
+#pragma unroll
+        for (int a2 = 1; a2 < A; ++a2) set &= rotr32(ss.m[k + a2], a2);
+        if (cx.queued > kStreamQueue - 32) stream_drain<A>(cx);
+        const unsigned mask = __ballot_sync(0xffffffffu, set != 0);
+        if (set) {
+            const int slot = cx.queued + __popc(mask & ((1u << lane) - 1u));
+            cx.qpos[slot] = pos + k;
+            cx.qset[slot] = set;
+        }
+        cx.queued += __popc(mask);
+    }
+}
+
+template <int A>
+__global__ void __launch_bounds__(kStreamThreads, 3)
+fragment_stream_kernel(const int *__restrict__ ticks, long long n_vals, long long n_padded,
+                       const long long *__restrict__ off, const int *__restrict__ block_row, long long n_rows,
+                       const __grid_constant__ FragQuery fq, int shift, unsigned long long *__restrict__ keys) {
+    static_assert(A >= 2 && A <= kMaxAnchor, "anchor length");
+    __shared__ StreamSmem sm;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qn = fq.qn;
+    const int ng = qn - 1;                      // query intervals (>= A, checked by the host)
+    const unsigned last_bucket = static_cast<unsigned>((kGapRange >> shift) - 1);
+    for (int i = threadIdx.x; i < kMaxBuckets; i += kStreamThreads) sm.table[i] = 0u;
+    for (int i = threadIdx.x; i < qn; i += kStreamThreads) sm.q[i] = fq.q[i];
+    __syncthreads();
+    // query interval i marks every bucket that holds a length within tol_gap of it
+    // (bucket B = lengths [B << shift, (B+1) << shift), the last one: everything above)
+    for (int i = threadIdx.x; i < ng; i += kStreamThreads) {
+        const long long g = static_cast<long long>(sm.q[i + 1]) - sm.q[i];
+        const long long lo = max(0ll, g - fq.tol_gap) >> shift, hi = (g + fq.tol_gap) >> shift;
+        const unsigned b0 = static_cast<unsigned>(min(lo, static_cast<long long>(last_bucket)));
+        const unsigned b1 = static_cast<unsigned>(min(hi, static_cast<long long>(last_bucket)));
+        for (unsigned b = b0; b <= b1; ++b) atomicOr(&sm.table[b], 1u << (i & 31));
+    }
+    __syncthreads();
+
+    StreamCtx cx{ticks, off, block_row, keys, sm.q, sm.qpos[warp], sm.qset[warp], n_vals, qn, fq.tol, fq.tol_gap,
+                 fq.min_match, 0};
+
+    auto bucket_set = [&](int g) -> unsigned {  // negative (row-straddling) intervals land in the last bucket
+        return sm.table[min(static_cast<unsigned>(g) >> shift, last_bucket)];
+    };
+
+    const long long stride = static_cast<long long>(gridDim.x) * kCtaChunk;
+    long long base = static_cast<long long>(blockIdx.x) * kCtaChunk + warp * kWarpChunk;  // this warp's first tick
+    I32x8 v[kStreamUnits];
+    if (base < n_padded) {
+#pragma unroll
+        for (int u = 0; u < kStreamUnits; ++u) v[u] = ld_stream_ticks(ticks + base + u * kUnitTicks + lane * 8);
+    }
+    const int next_lane = (lane + 1) & 31;
+    for (; base < n_padded; base += stride) {
+        const bool more = base + stride < n_padded;
+        int la[A];  // the A ticks behind this warp's chunk (the array is padded past n_padded)
+#pragma unroll
+        for (int k = 0; k < A; ++k) la[k] = __ldg(ticks + base + kWarpChunk + k);
+#pragma unroll
+        for (int u = 0; u < kStreamUnits; ++u) {
+            // Lane L needs tick 8 and the sets 8 .. 8+A-2 of its run from lane L+1; lane 31 from lane 0
+            // of the NEXT unit, whose registers lane 0 still holds -- lane 0 publishes those instead of
+            // its own (nobody reads lane 0's own).
+            int nx[A];
+#pragma unroll
+            for (int k = 0; k < A; ++k) nx[k] = u + 1 < kStreamUnits ? v[(u + 1) % kStreamUnits].t[k] : la[k];
+            unsigned m[8 + A - 1];
+            const int t8 = __shfl_sync(0xffffffffu, lane == 0 ? nx[0] : v[u].t[0], next_lane);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) m[k] = bucket_set(v[u].t[k + 1] - v[u].t[k]);
+            m[7] = bucket_set(t8 - v[u].t[7]);
+#pragma unroll
+            for (int k = 0; k < A - 1; ++k) {
+                const unsigned nxset = bucket_set(nx[k + 1] - nx[k]);
+                m[8 + k] = __shfl_sync(0xffffffffu, lane == 0 ? nxset : m[k], next_lane);
+            }
+            unsigned flags = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                unsigned hit = m[k];
+#pragma unroll
+                for (int a2 = 1; a2 < A; ++a2) hit &= rotr32(m[k + a2], a2);
+                flags |= (hit != 0u) << k;
+            }
+            const unsigned any = __reduce_or_sync(0xffffffffu, flags);
+            if (any) {  // rare: one out-of-line call per unit keeps the streaming loop's registers free
+                StreamSets ss;
+#pragma unroll
+                for (int k = 0; k < 8 + A - 1; ++k) ss.m[k] = m[k];
+                stream_park_unit<A>(cx, ss, any, base + u * kUnitTicks + lane * 8);
+            }
+            if (more) v[u] = ld_stream_ticks(ticks + base + stride + u * kUnitTicks + lane * 8);
+        }
+    }
+    stream_drain<A>(cx);
+}
+
 }  // namespace
 }  // namespace tvz
 
@@ -255,9 +486,12 @@ struct tvz_fragcat {
     int device = 0;
     double tick_hz = 1000.0;
     long long n_rows = 0, n_vals = 0;
+    long long n_padded = 0;                       // ticks are padded to whole streaming chunks (+ 8 look-ahead)
     int *d_ticks = nullptr;
     long long *d_off = nullptr;
     int *d_vid = nullptr;
+    int *d_block_row = nullptr;                   // row holding tick b * 256 (streaming kernel: survivor -> row)
+    unsigned long long *d_keys = nullptr;         // [n_rows] best-candidate keys, zero between queries
     // workspace (calls on one catalogue are serialised by `mu`)
     std::mutex mu;
     long long cap = 0;
@@ -295,10 +529,11 @@ int frag_reserve(tvz_fragcat *c, long long cap) {
     return TVZ_OK;
 }
 
-int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int tol, int tol_gap, int zero_only,
-                 int *d_out, long long out_cap, cudaStream_t st) {
+int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int tol, int tol_gap, int anchor,
+                 int zero_only, int *d_out, long long out_cap, cudaStream_t st) {
     TVZ_REQUIRE(qn >= 0 && (qn == 0 || h_q), "bad query");
     TVZ_REQUIRE(tol >= 0 && tol_gap >= 0, "negative tolerance");
+    TVZ_REQUIRE(anchor >= 1 && anchor <= kMaxAnchor, "anchor_intervals must be 1..%d", kMaxAnchor);
     FragQuery fq{};
     std::vector<int> q;
     q.reserve(qn);
@@ -324,6 +559,22 @@ int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int t
     while ((1ll << shift) <= tol_gap && shift < 30) ++shift;
     TVZ_REQUIRE((kGapRange >> shift) >= 1, "tol_gap %d too large", tol_gap);
     fq.min_match = min_match;
+    if (!zero_only && anchor >= 2) {
+        // streaming kernel; a query with fewer than `anchor` intervals generates no candidate at all
+        if (fq.qn - 1 >= anchor) {
+            const long long chunks = c->n_padded / kCtaChunk;
+            const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, 3ll * num_sms())));
+            if (anchor == 2)
+                fragment_stream_kernel<2><<<grid, kStreamThreads, 0, st>>>(c->d_ticks, c->n_vals, c->n_padded, c->d_off,
+                                                                          c->d_block_row, c->n_rows, fq, shift, c->d_keys);
+            else
+                fragment_stream_kernel<3><<<grid, kStreamThreads, 0, st>>>(c->d_ticks, c->n_vals, c->n_padded, c->d_off,
+                                                                          c->d_block_row, c->n_rows, fq, shift, c->d_keys);
+            TVZ_CUDA(cudaGetLastError());
+        }
+        return compact_enqueue_keys(c->d_keys, c->n_rows, min_match, c->d_vid, d_out, c->d_rows, out_cap, c->d_nhits,
+                                    c->d_state, c->d_ticket, d_out + 2 * (out_cap + 1), st);
+    }
     const long long want = (c->n_rows + kFragWarps - 1) / kFragWarps;
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, 4ll * num_sms())));
     fragment_match_kernel<<<grid, kFragThreads, 0, st>>>(c->d_ticks, c->d_off, c->n_rows, fq, shift, c->d_score,
@@ -368,6 +619,18 @@ int tvz_fragcat_create(const double *h_ts, const int64_t *h_off, const int32_t *
     c->tick_hz = tick_hz;
     c->n_rows = n_rows;
     c->n_vals = static_cast<long long>(ticks.size());
+    c->n_padded = (c->n_vals + kCtaChunk - 1) / kCtaChunk * kCtaChunk;
+    ticks.resize(static_cast<size_t>(c->n_padded) + 8, kPadTick);
+    // coarse index: last row whose offset is <= b * 256 (clamped to the last row)
+    std::vector<int> block_row(static_cast<size_t>(c->n_padded >> kStreamBlockShift) + 2, 0);
+    {
+        long long r = 0;
+        for (size_t b = 0; b < block_row.size(); ++b) {
+            const long long e = static_cast<long long>(b) << kStreamBlockShift;
+            while (r + 1 < n_rows && off[r + 1] <= e) ++r;
+            block_row[b] = static_cast<int>(r);
+        }
+    }
     cudaGetDevice(&c->device);
     auto fail = [&](cudaError_t e, const char *what) {
         set_error(TVZ_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
@@ -379,6 +642,11 @@ int tvz_fragcat_create(const double *h_ts, const int64_t *h_off, const int32_t *
     if ((e = cudaMalloc(&c->d_ticks, std::max<size_t>(1, ticks.size()) * 4)) != cudaSuccess) return fail(e, "cudaMalloc(ticks)");
     if ((e = cudaMalloc(&c->d_off, off.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(off)");
     if ((e = cudaMalloc(&c->d_vid, nr * 4)) != cudaSuccess) return fail(e, "cudaMalloc(vid)");
+    if ((e = cudaMalloc(&c->d_block_row, block_row.size() * 4)) != cudaSuccess) return fail(e, "cudaMalloc(block_row)");
+    if ((e = cudaMemcpy(c->d_block_row, block_row.data(), block_row.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(block_row)");
+    if ((e = cudaMalloc(&c->d_keys, nr * 8)) != cudaSuccess) return fail(e, "cudaMalloc(keys)");
+    if ((e = cudaMemset(c->d_keys, 0, nr * 8)) != cudaSuccess) return fail(e, "cudaMemset(keys)");
     if ((e = cudaMalloc(&c->d_score, nr * 4)) != cudaSuccess) return fail(e, "cudaMalloc(score)");
     if ((e = cudaMalloc(&c->d_delta, nr * 4)) != cudaSuccess) return fail(e, "cudaMalloc(delta)");
     if ((e = cudaMalloc(&c->d_nhits, 8)) != cudaSuccess) return fail(e, "cudaMalloc(nhits)");
@@ -412,7 +680,7 @@ void tvz_fragcat_destroy(tvz_fragcat *c) {
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->d_ticks, c->d_off, c->d_vid, c->d_score, c->d_delta, c->d_out, c->d_rows, c->d_nhits, c->d_state,
-                   c->d_ticket};
+                   c->d_ticket, c->d_block_row, c->d_keys};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (c->h_out) cudaFreeHost(c->h_out);
@@ -424,26 +692,28 @@ int64_t tvz_fragcat_rows(const tvz_fragcat *c) { return c ? c->n_rows : 0; }
 int64_t tvz_fragcat_values(const tvz_fragcat *c) { return c ? c->n_vals : 0; }
 
 int tvz_fragcat_match_async(tvz_fragcat *c, const double *h_q, int qn, int min_match, int tol_ticks,
-                            int tol_gap_ticks, int zero_offset_only, int32_t *d_out, int64_t out_cap, void *stream) {
+                            int tol_gap_ticks, int anchor_intervals, int zero_offset_only, int32_t *d_out,
+                            int64_t out_cap, void *stream) {
     return guarded([&]() -> int {
     TVZ_REQUIRE(c && d_out && out_cap >= 1, "bad arguments");
     std::lock_guard<std::mutex> lk(c->mu);
     int rc = frag_reserve(c, out_cap);  // d_rows must hold out_cap row indices
     if (rc) return rc;
-    return frag_enqueue(c, h_q, qn, min_match, tol_ticks, tol_gap_ticks, zero_offset_only, d_out, out_cap,
-                        static_cast<cudaStream_t>(stream));
+    return frag_enqueue(c, h_q, qn, min_match, tol_ticks, tol_gap_ticks, anchor_intervals, zero_offset_only, d_out,
+                        out_cap, static_cast<cudaStream_t>(stream));
     });
 }
 
 int tvz_fragcat_match(tvz_fragcat *c, const double *q, int qn, int min_match, int tol_ticks, int tol_gap_ticks,
-                      int zero_offset_only, int32_t *out_video_id, int32_t *out_score, int32_t *out_delta_ticks,
+                      int anchor_intervals, int zero_offset_only, int32_t *out_video_id, int32_t *out_score, int32_t *out_delta_ticks,
                       int64_t cap, int64_t *n_out) {
     return guarded([&]() -> int {
     TVZ_REQUIRE(c && n_out, "null pointer");
     *n_out = 0;
     TVZ_REQUIRE(cap >= 0 && (cap == 0 || (out_video_id && out_score && out_delta_ticks)), "bad output buffers");
     std::lock_guard<std::mutex> lk(c->mu);
-    int rc = frag_enqueue(c, q, qn, min_match, tol_ticks, tol_gap_ticks, zero_offset_only, c->d_out, c->cap, c->stream);
+    int rc = frag_enqueue(c, q, qn, min_match, tol_ticks, tol_gap_ticks, anchor_intervals, zero_offset_only, c->d_out,
+                          c->cap, c->stream);
     if (rc) return rc;
     TVZ_CUDA(cudaMemcpyAsync(c->h_out, c->d_out, 8, cudaMemcpyDeviceToHost, c->stream));
     TVZ_CUDA(cudaStreamSynchronize(c->stream));

@@ -312,12 +312,15 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// kKeys (fragment mode, streaming kernel): the per-row input is a packed u64 best-candidate key
+// (common.cuh: frag_key) instead of counts[] + aux[]; score = key >> 32, the offset is decoded.
+template <bool kKeys>
 __global__ void __launch_bounds__(kScanThreads)
 match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, const int *__restrict__ vid,
                      int *__restrict__ out, long long *__restrict__ rows_out, long long cap,
                      long long *__restrict__ n_hits_out, unsigned long long *state, unsigned *ticket,
                      const int *__restrict__ aux, int *__restrict__ aux_out, const __grid_constant__ GatherTargets gt,
-                     const BatchStrides bs) {
+                     const BatchStrides bs, unsigned long long *__restrict__ keys) {
     // batched queries: blockIdx.y picks the query, everything below is per query
     counts += blockIdx.y * bs.counts;
     out += blockIdx.y * bs.out;
@@ -343,13 +346,22 @@ match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, 
     const unsigned long long tag = static_cast<unsigned long long>(epoch) << 34;
     const long long r0 = blk * static_cast<long long>(kScanRowsPerBlock) + threadIdx.x * kScanRowsPerThread;
     int cnt[kScanRowsPerThread];
+    int dec[kKeys ? kScanRowsPerThread : 1];
     int mine = 0;
 #pragma unroll
     for (int j = 0; j < kScanRowsPerThread; ++j) {
         cnt[j] = -1;
         if (r0 + j < n_rows) {
-            const int c = counts[r0 + j];
-            if (c != 0) counts[r0 + j] = 0;
+            int c;
+            if (kKeys) {
+                const unsigned long long k = keys[r0 + j];
+                if (k != 0) keys[r0 + j] = 0;
+                c = frag_key_score(k);
+                dec[j] = frag_key_delta(k);
+            } else {
+                c = counts[r0 + j];
+                if (c != 0) counts[r0 + j] = 0;
+            }
             if (c >= min_match) { cnt[j] = c; ++mine; }
         }
     }
@@ -425,7 +437,9 @@ match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, 
                 out[2 + 2 * pos] = vid[r0 + j];
                 out[3 + 2 * pos] = cnt[j];
                 rows_out[pos] = r0 + j;
-                if (aux) aux_out[1 + pos] = aux[r0 + j];  // per-row payload (fragment mode: best offset)
+                // per-row payload (fragment mode: best offset)
+                if (kKeys) aux_out[1 + pos] = dec[j];
+                else if (aux) aux_out[1 + pos] = aux[r0 + j];
                 // fused gather: every block ships its own hits to all peers (8-byte stores over NVLink)
                 for (int p = 0; p < gt.n_peers; ++p)
                     *reinterpret_cast<int2 *>(gt.record[p] + 2 + 2 * pos) = make_int2(vid[r0 + j], cnt[j]);
@@ -509,9 +523,20 @@ int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid
                     long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket,
                     const int *aux, int *aux_out, cudaStream_t st, const GatherTargets *gather) {
     const GatherTargets none{};
-    match_compact_kernel<<<compact_blocks(n_rows), kScanThreads, 0, st>>>(counts, n_rows, min_match, vid, out, rows_out,
-                                                                          cap, n_hits_out, state, ticket, aux, aux_out,
-                                                                          gather ? *gather : none, BatchStrides{});
+    match_compact_kernel<false><<<compact_blocks(n_rows), kScanThreads, 0, st>>>(
+        counts, n_rows, min_match, vid, out, rows_out, cap, n_hits_out, state, ticket, aux, aux_out,
+        gather ? *gather : none, BatchStrides{}, nullptr);
+    TVZ_CUDA(cudaGetLastError());
+    return TVZ_OK;
+}
+
+// Same compaction over packed best-candidate keys (fragment streaming kernel); keys[] is zeroed.
+int compact_enqueue_keys(unsigned long long *keys, long long n_rows, int min_match, const int *vid, int *out,
+                         long long *rows_out, long long cap, long long *n_hits_out, unsigned long long *state,
+                         unsigned *ticket, int *delta_out, cudaStream_t st) {
+    match_compact_kernel<true><<<compact_blocks(n_rows), kScanThreads, 0, st>>>(
+        nullptr, n_rows, min_match, vid, out, rows_out, cap, n_hits_out, state, ticket, nullptr, delta_out,
+        GatherTargets{}, BatchStrides{}, keys);
     TVZ_CUDA(cudaGetLastError());
     return TVZ_OK;
 }
@@ -521,8 +546,9 @@ int compact_enqueue_batch(int *counts, long long n_rows, int min_match, const in
                           const BatchStrides &bs, cudaStream_t st) {
     const GatherTargets none{};
     dim3 grid(compact_blocks(n_rows), n_batch);
-    match_compact_kernel<<<grid, kScanThreads, 0, st>>>(counts, n_rows, min_match, vid, out, rows_out, cap, n_hits_out,
-                                                        state, ticket, nullptr, nullptr, none, bs);
+    match_compact_kernel<false><<<grid, kScanThreads, 0, st>>>(counts, n_rows, min_match, vid, out, rows_out, cap,
+                                                               n_hits_out, state, ticket, nullptr, nullptr, none, bs,
+                                                               nullptr);
     TVZ_CUDA(cudaGetLastError());
     return TVZ_OK;
 }

@@ -18,6 +18,7 @@ from .catalog import rows_to_csr
 DEFAULT_TICK_HZ = 1000.0      # 1 ms ticks
 DEFAULT_TOL = 7               # ticks: "%.6g" keeps 10 ms resolution above 1000 s (5 ms error) + rounding
 DEFAULT_TOL_GAP = 14
+DEFAULT_ANCHOR = 2            # consecutive agreeing intervals that nominate an offset (1 = most permissive, slower)
 
 
 class FragmentCatalogue:
@@ -48,7 +49,7 @@ class FragmentCatalogue:
         return cls(*rows_to_csr(rows), **kw)
 
     def match(self, clip_timestamps, min_match: int = 5, tol: int = DEFAULT_TOL, tol_gap: int = DEFAULT_TOL_GAP,
-              zero_offset_only: bool = False):
+              anchor: int = DEFAULT_ANCHOR, zero_offset_only: bool = False):
         """-> (video_id i32 [n], score i32 [n], offset_ticks i32 [n]) in catalogue order."""
         q = np.ascontiguousarray(np.asarray(clip_timestamps, dtype=np.float64).reshape(-1))
         n_out = C.c_int64(0)
@@ -57,7 +58,8 @@ class FragmentCatalogue:
             vid, sc, dl = (np.empty(cap, np.int32) for _ in range(3))
             with torch.cuda.device(self.device):
                 rc = lib().tvz_fragcat_match(self._handle, q.ctypes.data, q.shape[0], int(min_match), int(tol),
-                                             int(tol_gap), int(zero_offset_only), vid.ctypes.data, sc.ctypes.data,
+                                             int(tol_gap), int(anchor), int(zero_offset_only), vid.ctypes.data,
+                                             sc.ctypes.data,
                                              dl.ctypes.data, cap, C.byref(n_out))
             if rc == TVZ_ERR_OVERFLOW and n_out.value > cap:
                 self._cap = int(n_out.value)       # the library has grown its side; rerun
@@ -67,7 +69,8 @@ class FragmentCatalogue:
             return vid[:n], sc[:n], dl[:n]
 
     def match_async(self, clip_timestamps, min_match: int, out: torch.Tensor, tol: int = DEFAULT_TOL,
-                    tol_gap: int = DEFAULT_TOL_GAP, zero_offset_only: bool = False, stream=None) -> None:
+                    tol_gap: int = DEFAULT_TOL_GAP, anchor: int = DEFAULT_ANCHOR, zero_offset_only: bool = False,
+                    stream=None) -> None:
         """Enqueue on `stream`; `out`: int32 CUDA tensor [3 * (cap + 1)] (layout in include/tvidz_b200.h)."""
         if out.dtype != torch.int32 or out.dim() != 1 or out.numel() % 3 or not out.is_contiguous():
             raise ValueError("out must be a contiguous int32 [3 * (cap + 1)] tensor")
@@ -76,7 +79,7 @@ class FragmentCatalogue:
         st = torch.cuda.current_stream(self.device) if stream is None else stream
         with torch.cuda.device(self.device):
             check(lib().tvz_fragcat_match_async(self._handle, q.ctypes.data, q.shape[0], int(min_match), int(tol),
-                                                int(tol_gap), int(zero_offset_only), out.data_ptr(), cap,
+                                                int(tol_gap), int(anchor), int(zero_offset_only), out.data_ptr(), cap,
                                                 int(st.cuda_stream)))
 
     def find_fragments(self, clip_timestamps, min_match: int = 5, top_k: int | None = None, **kw):
