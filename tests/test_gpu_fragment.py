@@ -78,6 +78,26 @@ def test_streaming_kernel_ragged_rows_and_long_queries(cuda, anchor):
     cat.close()
 
 
+def test_survivor_queue_overflow_resolves_in_place(cuda, monkeypatch):
+    """A query that matches nearly everywhere fills a warp's survivor queue before the end of its
+    stream (forced tiny here): the early drains must give identical results."""
+    monkeypatch.setenv("TVZ_FRAG_QUEUE_CAP", "40")
+    rng = np.random.default_rng(9)
+    base = np.cumsum(rng.integers(15, 150, 3000)) / 30.0
+    rows = [(i + 1, (np.round((base[a:a + 400] + i) * 1000) / 1000).tolist())
+            for i, a in enumerate(rng.integers(0, 2600, 300))]
+    from tvidz_b200.catalog import rows_to_csr
+    ts, off, vid = rows_to_csr(rows)
+    cat = FragmentCatalogue(ts, off, vid, hit_capacity=512)
+    q = (np.round(base[1000:1030] * 1000) / 1000).tolist()
+    for _ in range(2):                                              # the queue is reset between queries
+        v, s, d = cat.match(q, 4)
+        want = oracle.find_fragments_csr(ts, off, vid, q, min_match=4)
+        assert list(zip(v.tolist(), s.tolist(), d.tolist())) == want
+    assert len(want) > 40
+    cat.close()
+
+
 def test_short_rows_tolerances_and_edges(cuda):
     rows = [(1, [0.5, 1.0, 2.5, 4.0]), (2, [100.5, 101.0, 102.5, 104.0, 250.0]), (3, []), (4, [7.0]),
             (5, [10.0, 10.5]), (6, [4.0, 2.5, 1.0, 0.5, 0.5, float("nan")]),        # unsorted, repeat, NaN

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtvidz_b200.so")
+# TVZ_LIB: tuning hook (scripts/sweep_fragment.py loads kernel-shape variants of the same library)
+LIB_PATH = os.environ.get("TVZ_LIB") or os.path.join(_HERE, "libtvidz_b200.so")
 
 # every symbol include/tvidz_b200.h declares: (name, restype, argtypes)
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double

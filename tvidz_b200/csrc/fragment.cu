@@ -31,6 +31,7 @@
 // into the hit list.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -256,25 +257,39 @@ fragment_match_kernel(const int *__restrict__ ticks, const long long *__restrict
 // anchor >= 2: streaming kernel.
 //
 // The tick array of the whole shard is read ONCE, front to back, regardless of row boundaries
-// (4 B per stored timestamp; `off` is touched only for survivors).  A warp owns 1024 consecutive
-// ticks per iteration as four 256-bit loads per lane (rolling prefetch: a unit's registers are
-// reloaded from the next chunk as soon as it has been tested).  Per tick: the interval to the next
+// (4 B per stored timestamp; `off` is touched only for survivors).  A warp owns 1536 consecutive
+// ticks per iteration as six 256-bit loads per lane (rolling prefetch: a unit's registers are
+// reloaded from the next chunk as soon as it has been tested; 16 warps x 6 KB in flight per SM,
+// 128 registers so that nothing spills -- measured sweep in profiles/r01_fragment_stream_sweep.txt).  Per tick: the interval to the next
 // tick indexes a 2048-entry shared-memory table whose entry is a 32-bit set of the query intervals
 // (index mod 32) that could agree with an interval in that bucket; position p survives iff some
 // query interval i is in the set of p, i+1 in the set of p+1 (, i+2 in the set of p+2):
 //     hit(p) = m[p] & rotr(m[p+1], 1) [& rotr(m[p+2], 2)]
-// -- a rotate and an AND per tick, one REDUX.OR per 256 ticks.  Intervals that straddle two rows
-// are garbage and are rejected with everything else when a survivor is resolved: row through the
-// coarse index + a short search in `off`, exact interval test against every query position the
-// set names, then the same anchored merge walk as the per-row kernel scores the offset and the
-// row's best candidate is combined across warps with one 64-bit atomicMax (frag_key).
-constexpr int kStreamThreads = 256;
+// -- a rotate and an AND per tick, one warp vote per 256 ticks.  Survivors (~0.05 % of positions)
+// are parked in a per-warp shared-memory queue and resolved when the warp has finished streaming
+// (stream_drain).  Intervals that straddle two rows are garbage and are rejected with everything
+// else there: row through the coarse index + a short search in `off`, exact interval test against
+// every query position the set names, then the same anchored merge walk as the per-row kernel
+// scores the offset and the row's best candidate is combined across warps with one 64-bit
+// atomicMax (frag_key).
+// launch shape (overridable for tuning sweeps: scripts/sweep_fragment.py builds variants)
+#ifndef TVZ_FS_THREADS
+#define TVZ_FS_THREADS 256
+#endif
+#ifndef TVZ_FS_MINB
+#define TVZ_FS_MINB 2
+#endif
+#ifndef TVZ_FS_UNITS
+#define TVZ_FS_UNITS 6
+#endif
+constexpr int kStreamThreads = TVZ_FS_THREADS;
+constexpr int kStreamMinBlocks = TVZ_FS_MINB;
 constexpr int kStreamWarps = kStreamThreads / 32;
-constexpr int kStreamUnits = 4;                          // 256-bit loads in flight per thread
+constexpr int kStreamUnits = TVZ_FS_UNITS;                          // 256-bit loads in flight per thread
 constexpr int kUnitTicks = 32 * 8;                       // one warp-wide 256-bit load
-constexpr int kWarpChunk = kStreamUnits * kUnitTicks;    // 1024 consecutive ticks per warp per iteration
-constexpr int kCtaChunk = kStreamWarps * kWarpChunk;     // 8192 ticks = 32 KB
-constexpr int kStreamQueue = 64;                         // survivors parked per warp
+constexpr int kWarpChunk = kStreamUnits * kUnitTicks;    // 1536 consecutive ticks per warp per iteration
+constexpr int kCtaChunk = kStreamWarps * kWarpChunk;     // 12288 ticks = 48 KB
+constexpr int kStreamQueue = 256 + 64;                   // survivors parked per warp (>= the 256 one unit can add)
 constexpr int kStreamBlockShift = 8;                     // coarse row index: one entry per 256 ticks
 constexpr int kMaxAnchor = 3;
 constexpr int kPadTick = 0x7fffffff;
@@ -315,10 +330,6 @@ struct StreamCtx {
     unsigned *qset;
     long long n_vals;
     int qn, tol, tol_gap, min_match;
-    int queued;            // warp-uniform, <= kStreamQueue
-};
-struct StreamSets {
-    unsigned m[8 + kMaxAnchor - 1];
 };
 
 // Survivor at flat position `pos` whose set names the query intervals (mod 32) that may start an
@@ -360,69 +371,54 @@ __device__ __forceinline__ void stream_resolve(const StreamCtx &cx, long long po
     if (best) atomicMax(&cx.keys[a], best);
 }
 
-// Resolve the warp's parked survivors, 32 at a time (called by the whole warp).
+// Resolve the warp's parked survivors, 32 at a time (called by the whole warp).  Normally this
+// runs ONCE, after the warp's last chunk: a warp meets a few dozen survivors over its whole share
+// of the catalogue, the queue holds 320, and at that point every warp of the grid is resolving at
+// the same time, so the dependent loads of one survivor hide behind those of ~75,000 others.
+// Only a query that matches nearly everywhere fills the queue earlier.
 template <int A>
-__device__ __noinline__ void stream_drain(StreamCtx &cx) {
+__device__ __noinline__ void stream_drain(const StreamCtx &cx, int n) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
-    for (int i = lane; i < cx.queued; i += 32) stream_resolve<A>(cx, cx.qpos[i], cx.qset[i]);
+    for (int i = lane; i < n; i += 32) stream_resolve<A>(cx, cx.qpos[i], cx.qset[i]);
     __syncwarp();
-    cx.queued = 0;
-}
-
-// A unit (8 consecutive ticks per lane) in which some lane has a surviving position: park them.
-// Slots come from the vote mask (no atomics); the queue is drained first whenever a full warp's
-// worth might not fit.
-template <int A>
-__device__ __noinline__ void stream_park_unit(StreamCtx &cx, const StreamSets &ss, unsigned any, long long pos) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (!(any & (1u << k))) continue;
-        unsigned set = ss.m[k];
-#pragma unroll
-        for (int a2 = 1; a2 < A; ++a2) set &= rotr32(ss.m[k + a2], a2);
-        if (cx.queued > kStreamQueue - 32) stream_drain<A>(cx);
-        const unsigned mask = __ballot_sync(0xffffffffu, set != 0);
-        if (set) {
-            const int slot = cx.queued + __popc(mask & ((1u << lane) - 1u));
-            cx.qpos[slot] = pos + k;
-            cx.qset[slot] = set;
-        }
-        cx.queued += __popc(mask);
-    }
 }
 
 template <int A>
-__global__ void __launch_bounds__(kStreamThreads, 3)
+__global__ void __launch_bounds__(kStreamThreads, kStreamMinBlocks)
 fragment_stream_kernel(const int *__restrict__ ticks, long long n_vals, long long n_padded,
                        const long long *__restrict__ off, const int *__restrict__ block_row, long long n_rows,
-                       const __grid_constant__ FragQuery fq, int shift, unsigned long long *__restrict__ keys) {
+                       const __grid_constant__ FragQuery fq, int shift, unsigned long long *__restrict__ keys,
+                       int l2_ahead, int queue_cap) {
     static_assert(A >= 2 && A <= kMaxAnchor, "anchor length");
     __shared__ StreamSmem sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qn = fq.qn;
     const int ng = qn - 1;                      // query intervals (>= A, checked by the host)
-    const unsigned last_bucket = static_cast<unsigned>((kGapRange >> shift) - 1);
     for (int i = threadIdx.x; i < kMaxBuckets; i += kStreamThreads) sm.table[i] = 0u;
     for (int i = threadIdx.x; i < qn; i += kStreamThreads) sm.q[i] = fq.q[i];
     __syncthreads();
-    // query interval i marks every bucket that holds a length within tol_gap of it
-    // (bucket B = lengths [B << shift, (B+1) << shift), the last one: everything above)
+    // An interval of length g lives in bucket (g >> shift) mod 2048 -- long intervals (and the negative
+    // garbage between two rows) simply wrap around; query interval i marks every bucket that holds a
+    // length within tol_gap of it, so wrapping can add false survivors but never lose a true one.
     for (int i = threadIdx.x; i < ng; i += kStreamThreads) {
         const long long g = static_cast<long long>(sm.q[i + 1]) - sm.q[i];
-        const long long lo = max(0ll, g - fq.tol_gap) >> shift, hi = (g + fq.tol_gap) >> shift;
-        const unsigned b0 = static_cast<unsigned>(min(lo, static_cast<long long>(last_bucket)));
-        const unsigned b1 = static_cast<unsigned>(min(hi, static_cast<long long>(last_bucket)));
-        for (unsigned b = b0; b <= b1; ++b) atomicOr(&sm.table[b], 1u << (i & 31));
+        const long long lo = max(0ll, g - fq.tol_gap) >> shift, hi = (g + fq.tol_gap) >> shift;  // <= 3 buckets
+        for (long long b = lo; b <= hi; ++b) atomicOr(&sm.table[b & (kMaxBuckets - 1)], 1u << (i & 31));
     }
     __syncthreads();
 
-    StreamCtx cx{ticks, off, block_row, keys, sm.q, sm.qpos[warp], sm.qset[warp], n_vals, qn, fq.tol, fq.tol_gap,
-                 fq.min_match, 0};
+    const StreamCtx cx{ticks, off, block_row, keys, sm.q, sm.qpos[warp], sm.qset[warp], n_vals, qn, fq.tol, fq.tol_gap,
+                       fq.min_match};
+    long long *qpos = sm.qpos[warp];
+    unsigned *qset = sm.qset[warp];
+    int queued = 0;  // warp-uniform, <= kStreamQueue
 
-    auto bucket_set = [&](int g) -> unsigned {  // negative (row-straddling) intervals land in the last bucket
-        return sm.table[min(static_cast<unsigned>(g) >> shift, last_bucket)];
+    // byte offset of the bucket straight from the interval: one shift, one mask, LDS [reg + imm]
+    const int byte_shift = shift - 2;
+    auto bucket_set = [&](int g) -> unsigned {
+        const unsigned byte = (static_cast<unsigned>(g) >> byte_shift) & ((kMaxBuckets - 1) << 2);
+        return *reinterpret_cast<const unsigned *>(reinterpret_cast<const unsigned char *>(sm.table) + byte);
     };
 
     const long long stride = static_cast<long long>(gridDim.x) * kCtaChunk;
@@ -433,11 +429,22 @@ fragment_stream_kernel(const int *__restrict__ ticks, long long n_vals, long lon
         for (int u = 0; u < kStreamUnits; ++u) v[u] = ld_stream_ticks(ticks + base + u * kUnitTicks + lane * 8);
     }
     const int next_lane = (lane + 1) & 31;
+    int la[A], la_next[A];  // the A ticks behind this warp's chunk (the array is padded past n_padded)
+#pragma unroll
+    for (int k = 0; k < A; ++k) la_next[k] = base < n_padded ? __ldg(ticks + base + kWarpChunk + k) : 0;
     for (; base < n_padded; base += stride) {
         const bool more = base + stride < n_padded;
-        int la[A];  // the A ticks behind this warp's chunk (the array is padded past n_padded)
+        // optional (off by default, it did not pay): HBM -> L2 `l2_ahead` iterations ahead, one TMA
+        // prefetch of the warp's whole chunk
+        if (l2_ahead > 0 && lane == 0 && base + l2_ahead * stride < n_padded)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ticks + base + l2_ahead * stride),
+                         "r"(kWarpChunk * 4)
+                         : "memory");
 #pragma unroll
-        for (int k = 0; k < A; ++k) la[k] = __ldg(ticks + base + kWarpChunk + k);
+        for (int k = 0; k < A; ++k) {
+            la[k] = la_next[k];
+            if (more) la_next[k] = __ldg(ticks + base + stride + kWarpChunk + k);
+        }
 #pragma unroll
         for (int u = 0; u < kStreamUnits; ++u) {
             // Lane L needs tick 8 and the sets 8 .. 8+A-2 of its run from lane L+1; lane 31 from lane 0
@@ -456,25 +463,60 @@ fragment_stream_kernel(const int *__restrict__ ticks, long long n_vals, long lon
                 const unsigned nxset = bucket_set(nx[k + 1] - nx[k]);
                 m[8 + k] = __shfl_sync(0xffffffffu, lane == 0 ? nxset : m[k], next_lane);
             }
-            unsigned flags = 0;
+            unsigned acc = 0;  // OR of the 8 positions' surviving sets: a rotate and one LOP3 per tick
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 unsigned hit = m[k];
 #pragma unroll
-                for (int a2 = 1; a2 < A; ++a2) hit &= rotr32(m[k + a2], a2);
-                flags |= (hit != 0u) << k;
+                for (int a2 = 1; a2 < A - 1; ++a2) hit &= rotr32(m[k + a2], a2);
+                acc |= hit & rotr32(m[k + A - 1], A - 1);
             }
-            const unsigned any = __reduce_or_sync(0xffffffffu, flags);
-            if (any) {  // rare: one out-of-line call per unit keeps the streaming loop's registers free
-                StreamSets ss;
+#ifdef TVZ_FS_NOPARK
+            if (acc == 0xdeadbeefu) {
+#else
+            if (__any_sync(0xffffffffu, acc != 0u)) {
+#endif
+                // Rare path (inline, registers only): every lane re-derives which of its 8 positions
+                // survived, a shuffle scan hands out queue slots, the lanes park (position, set).
+                unsigned flags = 0;
 #pragma unroll
-                for (int k = 0; k < 8 + A - 1; ++k) ss.m[k] = m[k];
-                stream_park_unit<A>(cx, ss, any, base + u * kUnitTicks + lane * 8);
+                for (int k = 0; k < 8; ++k) {
+                    unsigned hit = m[k];
+#pragma unroll
+                    for (int a2 = 1; a2 < A; ++a2) hit &= rotr32(m[k + a2], a2);
+                    flags |= (hit != 0u) << k;
+                }
+                const int mine = __popc(flags);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += n;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (queued + total > queue_cap) {  // make room (a unit adds at most 256, the queue holds 320)
+                    stream_drain<A>(cx, queued);
+                    queued = 0;
+                }
+                int slot = queued + incl - mine;
+                const long long pos = base + u * kUnitTicks + lane * 8;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (flags & (1u << k)) {
+                        unsigned hit = m[k];
+#pragma unroll
+                        for (int a2 = 1; a2 < A; ++a2) hit &= rotr32(m[k + a2], a2);
+                        qpos[slot] = pos + k;
+                        qset[slot] = hit;
+                        ++slot;
+                    }
+                }
+                queued += total;
             }
             if (more) v[u] = ld_stream_ticks(ticks + base + stride + u * kUnitTicks + lane * 8);
         }
     }
-    stream_drain<A>(cx);
+    stream_drain<A>(cx, queued);
 }
 
 }  // namespace
@@ -563,13 +605,22 @@ int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int t
         // streaming kernel; a query with fewer than `anchor` intervals generates no candidate at all
         if (fq.qn - 1 >= anchor) {
             const long long chunks = c->n_padded / kCtaChunk;
-            const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, 3ll * num_sms())));
+            // test hook: TVZ_FRAG_QUEUE_CAP=<n> (>= 0, < 64) forces early in-place drains
+            int queue_cap = kStreamQueue;
+            if (const char *env = getenv("TVZ_FRAG_QUEUE_CAP")) queue_cap = std::min(64, std::max(0, atoi(env)));
+            static const int l2_ahead = [] {  // tuning hook: TVZ_FRAG_L2_AHEAD=<n> turns the L2 prefetch on
+                const char *e = getenv("TVZ_FRAG_L2_AHEAD");
+                return e ? atoi(e) : 0;  // measured: 0.115 ms without, 0.121 ms with (distance 1..4)
+            }();
+            const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, static_cast<long long>(kStreamMinBlocks) * num_sms())));
             if (anchor == 2)
                 fragment_stream_kernel<2><<<grid, kStreamThreads, 0, st>>>(c->d_ticks, c->n_vals, c->n_padded, c->d_off,
-                                                                          c->d_block_row, c->n_rows, fq, shift, c->d_keys);
+                                                                          c->d_block_row, c->n_rows, fq, shift, c->d_keys,
+                                                                          l2_ahead, queue_cap);
             else
                 fragment_stream_kernel<3><<<grid, kStreamThreads, 0, st>>>(c->d_ticks, c->n_vals, c->n_padded, c->d_off,
-                                                                          c->d_block_row, c->n_rows, fq, shift, c->d_keys);
+                                                                          c->d_block_row, c->n_rows, fq, shift, c->d_keys,
+                                                                          l2_ahead, queue_cap);
             TVZ_CUDA(cudaGetLastError());
         }
         return compact_enqueue_keys(c->d_keys, c->n_rows, min_match, c->d_vid, d_out, c->d_rows, out_cap, c->d_nhits,
