@@ -1,7 +1,44 @@
-"""Compare the count-kernel variants on the bench catalogue (1M rows): kernel time via the
-library's own CUDA events, whole query via torch events."""
-import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+"""Compare launch shapes / layouts of the count kernel on the bench catalogue (1M rows).
+
+  python scripts/sweep_match.py build            # here (no GPU): one library per variant under build/variants/
+  python scripts/sweep_match.py run [rows]       # on the GPU box: runs every variant (TVZ_LIB hook of _lib.py)
+  python scripts/sweep_match.py [rows] [nohit]   # times the library that is loaded: kernel time via the
+                                                 # library's own CUDA events, whole query via torch events
+"""
+import sys, os, subprocess
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VAR_DIR = os.path.join(ROOT, "build", "variants")
+VARIANTS = {            # name: (threads, units, extra defines)
+    "fp_t512_u4": (512, 4, []),
+    "fp_t512_u4_nolookup": (512, 4, ["-DTVZ_FP_NOLOOKUP"]),
+    "fp_t512_u4_nopark": (512, 4, ["-DTVZ_FP_NOPARK"]),
+    "fp_t512_u2": (512, 2, []),
+    "fp_t256_u8": (256, 8, []),
+    "fp_t256_u4": (256, 4, []),
+    "fp_t1024_u2": (1024, 2, []),
+}
+if len(sys.argv) > 1 and sys.argv[1] == "build":
+    from tvidz_b200 import build as b
+    os.makedirs(VAR_DIR, exist_ok=True)
+    for name, (t, u, extra) in VARIANTS.items():
+        out = os.path.join(VAR_DIR, f"libtvz_{name}.so")
+        cmd = [b.NVCC] + b.FLAGS + [f"-DTVZ_FP_THREADS={t}", f"-DTVZ_FP_UNITS={u}"] + extra + ["-Xptxas", "-v", "-o", out] + \
+            [os.path.join(b.CSRC, x) for x in b.SOURCES]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        lines = r.stderr.splitlines()
+        info = [lines[i + 1].strip().split("Function properties for ")[-1][:0] + lines[i + 2].strip() + " | " + lines[i + 3].strip()
+                for i, ln in enumerate(lines) if "match_count_kernelILb1" in ln and "Compiling" in ln]
+        print(name, "FAILED " + r.stderr[-300:] if r.returncode else info)
+    sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "run":
+    for name in VARIANTS:
+        lib = os.path.join(VAR_DIR, f"libtvz_{name}.so")
+        if os.path.exists(lib):
+            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[2:], capture_output=True, text=True,
+                               env=dict(os.environ, TVZ_LIB=lib))
+            print(f"{name:22s}", (r.stdout.strip().splitlines() or [r.stderr[-300:]])[-1], flush=True)
+    sys.exit(0)
 import numpy as np, torch
 from tvidz_b200 import _lib, synth
 from tvidz_b200.catalog import Catalogue

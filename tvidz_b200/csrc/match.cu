@@ -9,13 +9,15 @@
 //     ts   : uint64 [n_vals]  IEEE-754 bit patterns of the stored timestamps, canonicalised
 //            at pack time (-0.0 -> +0.0, NaN dropped, in-row repeats dropped) so that bitwise
 //            equality == Python float equality and every stored value can add at most once
+//     fp   : uint16 [n_vals]  filter_hash(ts[i]): what the single-query count kernel streams
 //     off  : int64 [n_rows+1] CSR row offsets into ts
 //     vid  : int32 [n_rows]   videos.id of each row
 // Because in-row repeats are gone, match_count(row) = sum over stored values v of
 // mult(v), where mult(v) = number of query positions equal to v.  The count kernel is
-// therefore a pure streaming pass over `ts` (the only large array): 256-bit coalesced
-// loads, a 64 KB shared-memory byte map of the query rejects ~all values with one LDS.U8,
-// and the rare survivors are looked up exactly and added to counts[row] with a RED.
+// therefore a pure streaming pass: 256-bit coalesced loads, a 64 KB shared-memory byte map of
+// the query rejects ~all values with one LDS.U8, and the rare survivors are looked up exactly
+// and added to counts[row] with a RED.  One query streams the 2-byte fingerprints (`fp`) and
+// touches `ts` only for survivors; the batched kernel (8 queries per pass) streams `ts` itself.
 #include <algorithm>
 #include <unordered_set>
 #include <vector>
@@ -27,24 +29,16 @@ namespace {
 
 constexpr int kMapEntries = 1 << 16;         // byte-map filter of the query: 64 KB of shared memory
 constexpr int kMaxKeys = 2048;               // distinct query values per launch
-constexpr int kCountThreads = 512;
-constexpr int kCountUnroll = 8;              // 8 x 16 B (= 4 x 256-bit loads) in flight per thread
+constexpr int kCountThreads = 512;            // batched kernel (streams the 8-byte values)
+constexpr int kCountUnroll = 8;               // 8 x 16 B (= 4 x 256-bit loads) in flight per thread
 constexpr int kChunkPairs = kCountThreads * kCountUnroll;  // 4096 pairs = 8192 values per CTA iteration
 constexpr int kCountWarps = kCountThreads / 32;
 constexpr int kWarpQueue = 64;               // filter survivors parked per warp
-constexpr int kBlockShift = 8;               // coarse row index: one entry per 256 stored values
+constexpr int kBlockShift = 7;               // coarse row index: one entry per 128 stored values
 constexpr int kScanThreads = 256;
 constexpr int kScanRowsPerThread = 8;
 constexpr int kScanRowsPerBlock = kScanThreads * kScanRowsPerThread;
 constexpr unsigned long long kPadPattern = 0x7ff8dead0000beefull;  // a NaN: never equals a stored value
-
-struct alignas(16) CountSmem {
-    unsigned char map[kMapEntries];   // first: zeroed with 16-byte stores
-    unsigned long long keys[kMaxKeys];
-    unsigned long long qv[kCountWarps][kWarpQueue];
-    long long qe[kCountWarps][kWarpQueue];
-    int mult[kMaxKeys];
-};
 
 // Two IMADs and a shift: good enough on frame-quantised timestamps and on x.0 / x.5 values
 // (false-positive rate ~ n_keys / 65536, measured in DESIGN.md).
@@ -83,18 +77,141 @@ __device__ __forceinline__ U64x4 ld_stream_256(const void *p) {
     return r;
 }
 
+// Which 32-byte unit of the CTA's chunk thread t loads as its j-th (batched kernel).
+__device__ __forceinline__ int unit_index(int j) { return j * kCountThreads + threadIdx.x; }
+
+// ---- single query: streaming pass over the 16-bit FINGERPRINTS of the stored values ----
+//
+// The byte-map filter only ever looks at filter_hash(v), 16 bits of a value.  The catalogue
+// therefore also stores fp[i] = filter_hash(ts[i]) as a uint16 array (+2 B per stored value), and the
+// count kernel streams THAT: 2 bytes of HBM traffic per stored timestamp instead of 8 -- 128 MB
+// instead of 512 MB for the 1 M-row catalogue.  Nothing is lost: a fingerprint that passes the
+// filter (true matches + ~n_keys/65536 false positives, ~0.3 % of values) is verified against the
+// real 8-byte value, fetched from `ts` only then, with the exact key lookup as before.
+//
+// A warp-wide 256-bit load brings 512 fingerprints (16 per lane).  Units are dealt round-robin to
+// all warps of the grid (unit g = (it * kFpUnits + j) * n_warps + warp), so the grid sweeps one
+// contiguous window per load slot and every warp ends within one unit of every other.  Per
+// fingerprint: extract, LDS.U8, shift-or into the lane's 16-bit survivor mask; one vote per unit.
+// Survivors are parked inline (slots from a shuffle scan) as element indices in a per-warp queue and
+// resolved 32 at a time -- normally once, when the warp has finished streaming: load the value,
+// binary search of the sorted query keys, row through the coarse index + a short search in `off`,
+// RED.ADD counts[row] += mult.
+// launch shape (overridable for tuning sweeps: scripts/sweep_match.py builds variants)
+#ifndef TVZ_FP_THREADS
+#define TVZ_FP_THREADS 512
+#endif
+#ifndef TVZ_FP_UNITS
+#define TVZ_FP_UNITS 2   // measured: 2 -> 48.7 us, 4 -> 59.4 us (spills at 64 registers), 8 at 256 threads -> 53.2 us
+#endif
+constexpr int kFpThreads = TVZ_FP_THREADS;
+constexpr int kFpWarps = kFpThreads / 32;
+constexpr int kFpUnits = TVZ_FP_UNITS;       // 256-bit loads in flight per thread
+constexpr int kFpPerUnit = 32 * 16;          // fingerprints per warp-wide load
+constexpr int kFpQueue = 128;                // survivors parked per warp
+
+struct alignas(16) FpSmem {
+    unsigned char map[kMapEntries];   // first: zeroed with 16-byte stores
+    unsigned long long keys[kMaxKeys];
+    long long qe[kFpWarps][kFpQueue];
+    int mult[kMaxKeys];
+};
+
+struct U32x8 {
+    unsigned w[8];
+};
+__device__ __forceinline__ U32x8 ld_stream_u32x8(const void *p) {
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
+                 : "l"(p));
+    U32x8 r;
+    r.w[0] = static_cast<unsigned>(a); r.w[1] = static_cast<unsigned>(a >> 32);
+    r.w[2] = static_cast<unsigned>(b); r.w[3] = static_cast<unsigned>(b >> 32);
+    r.w[4] = static_cast<unsigned>(c); r.w[5] = static_cast<unsigned>(c >> 32);
+    r.w[6] = static_cast<unsigned>(d); r.w[7] = static_cast<unsigned>(d >> 32);
+    return r;
+}
+
+// What a survivor needs to be verified.
+struct FpCtx {
+    const unsigned long long *ts;
+    const long long *off;
+    const int *block_row;
+    int *counts;
+    long long n_vals, n_rows;
+    int n_keys;
+};
+
+// Verify one survivor: the value and the coarse row index are fetched together (both depend only
+// on the element index), the sorted query keys are searched in shared memory, and the row is picked
+// from four consecutive offsets loaded at once (a 256-value block rarely spans more rows; the
+// general case falls back to a binary search).  Three dependent memory round trips per survivor.
+__device__ __forceinline__ void fp_resolve(const FpCtx &cx, const FpSmem &sm, long long elem) {
+    if (elem >= cx.n_vals) return;  // padding
+    const unsigned long long v = __ldg(cx.ts + elem);
+    const long long b = elem >> kBlockShift;
+    long long a = __ldg(cx.block_row + b);
+    const long long z = __ldg(cx.block_row + b + 1) + 1;  // last row with off[row] <= elem is in [a, z)
+    int lo = 0, hi = cx.n_keys;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sm.keys[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= cx.n_keys || sm.keys[lo] != v) return;  // fingerprint collision
+    if (z - a <= 5) {
+        long long o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = __ldg(cx.off + min(a + 1 + k, cx.n_rows));
+        int step = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) step += (a + 1 + k < z) && (o[k] <= elem);  // off is non-decreasing
+        a += step;
+    } else {
+        long long zz = z;
+        while (zz - a > 1) {
+            const long long mid = (a + zz) >> 1;
+            if (__ldg(cx.off + mid) <= elem) a = mid; else zz = mid;
+        }
+    }
+    atomicAdd(&cx.counts[a], sm.mult[lo]);
+}
+
+// Verify the warp's parked survivors, 32 at a time (called by the whole warp).  Out of line for the
+// rare mid-stream call (a dense query filling the queue), inline for the one at the end of the stream.
+__device__ __forceinline__ void fp_drain_inline(const FpCtx &cx, const FpSmem &sm, const long long *qe, int n) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) fp_resolve(cx, sm, qe[i]);
+    __syncwarp();
+}
+__device__ __noinline__ void fp_drain(const FpCtx &cx, const FpSmem &sm, const long long *qe, int n) {
+    fp_drain_inline(cx, sm, qe, n);
+}
+
 template <bool kParamQuery>
-__global__ void __launch_bounds__(kCountThreads, 2)
-match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
-                   const unsigned long long *__restrict__ keys, const int *__restrict__ mult, int n_keys,
-                   const long long *__restrict__ off, const int *__restrict__ block_row, long long n_rows,
+__global__ void __launch_bounds__(kFpThreads, kFpThreads >= 1024 ? 1 : 2)
+match_count_kernel(const unsigned short *__restrict__ fp, long long n_units, const unsigned long long *__restrict__ ts,
+                   long long n_vals, const unsigned long long *__restrict__ keys, const int *__restrict__ mult,
+                   int n_keys, const long long *__restrict__ off, const int *__restrict__ block_row, long long n_rows,
                    int *__restrict__ counts, const __grid_constant__ SmallQuery sq) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CountSmem &sm = *reinterpret_cast<CountSmem *>(smem_raw);
-    for (int i = threadIdx.x; i < kMapEntries / 16; i += kCountThreads)
+    FpSmem &sm = *reinterpret_cast<FpSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the first loads do not depend on the query: issue them before the byte map is built
+    const long long n_warps = static_cast<long long>(gridDim.x) * kFpWarps;
+    const long long wg = static_cast<long long>(blockIdx.x) * kFpWarps + warp;
+    const unsigned short *lane_fp = fp + lane * 16;
+    U32x8 v[kFpUnits];
+#pragma unroll
+    for (int j = 0; j < kFpUnits; ++j) {
+        const long long g = j * n_warps + wg;
+        if (g < n_units) v[j] = ld_stream_u32x8(lane_fp + g * kFpPerUnit);
+    }
+    for (int i = threadIdx.x; i < kMapEntries / 16; i += kFpThreads)
         reinterpret_cast<uint4 *>(sm.map)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    for (int i = threadIdx.x; i < n_keys; i += kCountThreads) {
+    for (int i = threadIdx.x; i < n_keys; i += kFpThreads) {
         const unsigned long long k = kParamQuery ? sq.keys[i] : keys[i];
         sm.keys[i] = k;
         sm.mult[i] = kParamQuery ? sq.mult[i] : mult[i];
@@ -102,76 +219,57 @@ match_count_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    unsigned long long *qv = sm.qv[threadIdx.x >> 5];
-    long long *qe = sm.qe[threadIdx.x >> 5];
-    int queued = 0;  // warp-uniform
+    const FpCtx cx{ts, off, block_row, counts, n_vals, n_rows, n_keys};
+    long long *qe = sm.qe[warp];
+    int queued = 0;  // warp-uniform, <= kFpQueue
 
-    auto resolve = [&](unsigned long long v, long long elem) {
-        int lo = 0, hi = n_keys;  // keys sorted ascending as uint64
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (sm.keys[mid] < v) lo = mid + 1; else hi = mid;
-        }
-        if (lo >= n_keys || sm.keys[lo] != v) return;  // filter false positive
-        const long long b = elem >> kBlockShift;
-        long long a = block_row[b], z = block_row[b + 1] + 1;  // last row with off[row] <= elem is in [a, z)
-        while (z - a > 1) {
-            const long long mid = (a + z) >> 1;
-            if (off[mid] <= elem) a = mid; else z = mid;
-        }
-        atomicAdd(&counts[a], sm.mult[lo]);
-    };
-    auto drain = [&]() {
-        __syncwarp();
-        for (int i = lane; i < min(queued, kWarpQueue); i += 32) resolve(qv[i], qe[i]);
-        __syncwarp();
-        queued = 0;
-    };
-    // park the lanes whose value survived the filter (slots from the vote mask, no atomics)
-    auto park = [&](bool pass, unsigned long long x, long long elem) {
-        const unsigned mask = __ballot_sync(0xffffffffu, pass);
-        if (pass) {
-            const int slot = queued + __popc(mask & ((1u << lane) - 1u));
-            if (slot < kWarpQueue) { qv[slot] = x; qe[slot] = elem; }
-            else resolve(x, elem);  // queue full (dense matches): resolve in place
-        }
-        queued += __popc(mask);
-    };
-    // A chunk = 4096 pairs = 2048 units of 32 bytes; thread t owns units t, t+512, t+1024, t+1536.
-    // Rolling prefetch: as soon as a unit has been probed its registers are reloaded from the
-    // next chunk, so ~4 x 32 B per thread stay in flight without a second register buffer.
-    constexpr int kUnits = kCountUnroll / 2;
-    const long long stride = static_cast<long long>(gridDim.x) * kChunkPairs;
-    long long base = static_cast<long long>(blockIdx.x) * kChunkPairs;
-    const U64x4 *ts4 = reinterpret_cast<const U64x4 *>(ts2);
-    U64x4 v[kUnits];
-    if (base < n_pairs_padded) {
+    for (long long g0 = wg; g0 < n_units; g0 += kFpUnits * n_warps) {
 #pragma unroll
-        for (int j = 0; j < kUnits; ++j) v[j] = ld_stream_256(ts4 + (base >> 1) + j * kCountThreads + threadIdx.x);
-    }
-    for (; base < n_pairs_padded; base += stride) {
-        const bool more = base + stride < n_pairs_padded;
-        const U64x4 *next = ts4 + ((base + stride) >> 1) + threadIdx.x;
+        for (int j = 0; j < kFpUnits; ++j) {
+            const long long g = g0 + j * n_warps;
+            if (g >= n_units) break;  // warp-uniform
+            unsigned flags = 0;       // bit k: the lane's k-th fingerprint is in the query's byte map
 #pragma unroll
-        for (int j = 0; j < kUnits; ++j) {
-            unsigned m4 = static_cast<unsigned>(sm.map[filter_hash(v[j].a)]);
-            m4 |= static_cast<unsigned>(sm.map[filter_hash(v[j].b)]) << 1;
-            m4 |= static_cast<unsigned>(sm.map[filter_hash(v[j].c)]) << 2;
-            m4 |= static_cast<unsigned>(sm.map[filter_hash(v[j].d)]) << 3;
-            const unsigned any = __reduce_or_sync(0xffffffffu, m4);  // did any of the warp's 128 values survive?
-            if (any) {
-                const long long elem = 2 * base + 4 * (j * kCountThreads + threadIdx.x);
-                if (any & 1u) park(m4 & 1u, v[j].a, elem);
-                if (any & 2u) park((m4 >> 1) & 1u, v[j].b, elem + 1);
-                if (any & 4u) park((m4 >> 2) & 1u, v[j].c, elem + 2);
-                if (any & 8u) park((m4 >> 3) & 1u, v[j].d, elem + 3);
+            for (int k = 0; k < 8; ++k) {
+                const unsigned w = v[j].w[k];
+#ifdef TVZ_FP_NOLOOKUP   // tuning: streaming floor without the byte-map lookups
+                flags |= (w == 0x12345678u) << k;
+#else
+                flags |= static_cast<unsigned>(sm.map[w & 0xffffu]) << (2 * k);
+                flags |= static_cast<unsigned>(sm.map[w >> 16]) << (2 * k + 1);
+#endif
             }
-            if (more) v[j] = ld_stream_256(next + j * kCountThreads);
+#ifdef TVZ_FP_NOPARK     // tuning: lookups only, survivors dropped
+            if (flags == 0xdeadbeefu) qe[0] = 1;
+            flags = 0;
+#endif
+            // park the survivors' element indices, one per lane and round (a lane rarely holds two):
+            // slots from the vote mask, no atomics, no scan
+            unsigned mask = __ballot_sync(0xffffffffu, flags != 0u);
+            if (mask) {
+                const long long e0 = g * kFpPerUnit + lane * 16;
+                do {
+                    if (queued + __popc(mask) > kFpQueue) {
+                        fp_drain(cx, sm, qe, queued);
+                        queued = 0;
+                    }
+                    if (flags) {
+                        const long long e = e0 + (__ffs(flags) - 1);
+                        qe[queued + __popc(mask & ((1u << lane) - 1u))] = e;
+                        flags &= flags - 1;
+                        // what the verification will read first, on its way to L2 while the stream goes on
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ts + e));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(block_row + (e >> kBlockShift)));
+                    }
+                    queued += __popc(mask);
+                    mask = __ballot_sync(0xffffffffu, flags != 0u);
+                } while (mask);
+            }
+            const long long gn = g + kFpUnits * n_warps;
+            if (gn < n_units) v[j] = ld_stream_u32x8(lane_fp + gn * kFpPerUnit);
         }
-        if (queued >= kWarpQueue / 2) drain();
     }
-    drain();
+    fp_drain_inline(cx, sm, qe, queued);
 }
 
 // ---- batched queries: up to 8 find_duplicates calls answered by ONE pass over the catalogue ----
@@ -269,11 +367,11 @@ match_count_batch_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_p
     U64x4 v[kUnits];
     if (base < n_pairs_padded) {
 #pragma unroll
-        for (int j = 0; j < kUnits; ++j) v[j] = ld_stream_256(ts4 + (base >> 1) + j * kCountThreads + threadIdx.x);
+        for (int j = 0; j < kUnits; ++j) v[j] = ld_stream_256(ts4 + (base >> 1) + unit_index(j));
     }
     for (; base < n_pairs_padded; base += stride) {
         const bool more = base + stride < n_pairs_padded;
-        const U64x4 *next = ts4 + ((base + stride) >> 1) + threadIdx.x;
+        const U64x4 *next = ts4 + ((base + stride) >> 1);
 #pragma unroll
         for (int j = 0; j < kUnits; ++j) {
             const unsigned ma = sm.map[filter_hash(v[j].a)], mb = sm.map[filter_hash(v[j].b)];
@@ -281,14 +379,14 @@ match_count_batch_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_p
             const unsigned any = __reduce_or_sync(0xffffffffu, (ma != 0) | ((mb != 0) << 1) | ((mc != 0) << 2) |
                                                                    ((md != 0) << 3));
             if (any) {
-                const long long elem = 2 * base + 4 * (j * kCountThreads + threadIdx.x);
+                const long long elem = 2 * base + 4 * unit_index(j);
                 if (any & 1u) park(ma, v[j].a, elem);
                 if (any & 2u) park(mb, v[j].b, elem + 1);
                 if (any & 4u) park(mc, v[j].c, elem + 2);
                 if (any & 8u) park(md, v[j].d, elem + 3);
                 if (queued >= kWarpQueue / 2) drain();
             }
-            if (more) v[j] = ld_stream_256(next + j * kCountThreads);
+            if (more) v[j] = ld_stream_256(next + unit_index(j));
         }
     }
     drain();
@@ -568,6 +666,8 @@ struct tvz_catalog {
     long long n_rows = 0, n_vals = 0, n_pairs = 0;
     long long n_pairs_padded = 0;  // ts is padded with a NaN pattern to whole count-kernel chunks
     unsigned long long *d_ts = nullptr;
+    unsigned short *d_fp = nullptr;  // filter_hash of every stored value, padded to whole 512-value units
+    long long n_units = 0;
     long long *d_off = nullptr;
     int *d_vid = nullptr;
     int *d_block_row = nullptr;    // row holding stored value b*1024 (coarse index for hit -> row)
@@ -696,6 +796,10 @@ int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *
             block_row[b] = static_cast<int>(r);
         }
     }
+    // 16-bit fingerprints, padded to whole warp units (pad entries point past n_vals and are dropped)
+    c->n_units = (c->n_vals + kFpPerUnit - 1) / kFpPerUnit;
+    std::vector<unsigned short> fp(static_cast<size_t>(std::max<long long>(1, c->n_units)) * kFpPerUnit, 0);
+    for (long long i = 0; i < c->n_vals; ++i) fp[i] = static_cast<unsigned short>(filter_hash(ts[i]));
     cudaGetDevice(&c->device);
     auto fail = [&](cudaError_t e, const char *what) {
         set_error(TVZ_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
@@ -704,6 +808,9 @@ int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *
     };
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_ts, ts.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(ts)");
+    if ((e = cudaMalloc(&c->d_fp, fp.size() * 2)) != cudaSuccess) return fail(e, "cudaMalloc(fp)");
+    if ((e = cudaMemcpy(c->d_fp, fp.data(), fp.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(fp)");
     if ((e = cudaMalloc(&c->d_off, off.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(off)");
     if ((e = cudaMalloc(&c->d_vid, std::max<size_t>(1, n_rows) * 4)) != cudaSuccess) return fail(e, "cudaMalloc(vid)");
     if ((e = cudaMalloc(&c->d_block_row, block_row.size() * 4)) != cudaSuccess) return fail(e, "cudaMalloc(block_row)");
@@ -724,6 +831,7 @@ int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *
 void tvz_catalog_destroy(tvz_catalog *c) {
     if (!c) return;
     if (c->d_ts) cudaFree(c->d_ts);
+    if (c->d_fp) cudaFree(c->d_fp);
     if (c->d_off) cudaFree(c->d_off);
     if (c->d_vid) cudaFree(c->d_vid);
     if (c->d_block_row) cudaFree(c->d_block_row);
@@ -859,20 +967,25 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
         ++nk;
         i = j;
     }
-    if (want_kth && qn > 0)
+    // The pinned staging buffer is read by the device only when a copy out of it is enqueued; the
+    // common case (a short query riding in the kernel parameters) never is, so back-to-back
+    // asynchronous queries pipeline on the stream without a host-side wait in between.
+    bool staged_copy = false;
+    if (want_kth && qn > 0) {
         TVZ_CUDA(cudaMemcpyAsync(ws->d_qcanon, h_qc, sizeof(unsigned long long) * qn, cudaMemcpyHostToDevice, st));
+        staged_copy = true;
+    }
     if (cat->n_rows > 0) {
         const int sms = num_sms();
-        const long long chunks = cat->n_pairs_padded / kChunkPairs;
-        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, 2ll * sms)));
-        const ulonglong2 *ts2 = reinterpret_cast<const ulonglong2 *>(cat->d_ts);
+        const long long want = (cat->n_units + kFpWarps - 1) / kFpWarps;   // at least one unit per warp
+        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, 2ll * sms)));
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
         auto launch = [&](bool param, const unsigned long long *dk, const int *dm, int n, const SmallQuery &sq) -> int {
             auto kern = param ? match_count_kernel<true> : match_count_kernel<false>;
             TVZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(sizeof(CountSmem))));
-            kern<<<grid, kCountThreads, sizeof(CountSmem), st>>>(ts2, cat->n_pairs_padded, dk, dm, n, cat->d_off,
-                                                                 cat->d_block_row, cat->n_rows, ws->d_counts, sq);
+                                          static_cast<int>(sizeof(FpSmem))));
+            kern<<<grid, kFpThreads, sizeof(FpSmem), st>>>(cat->d_fp, cat->n_units, cat->d_ts, cat->n_vals, dk, dm, n,
+                                                           cat->d_off, cat->d_block_row, cat->n_rows, ws->d_counts, sq);
             TVZ_CUDA(cudaGetLastError());
             return TVZ_OK;
         };
@@ -890,6 +1003,7 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
                 TVZ_CUDA(cudaMemcpyAsync(ws->d_keys, h_keys + k0, sizeof(unsigned long long) * n,
                                          cudaMemcpyHostToDevice, st));
                 TVZ_CUDA(cudaMemcpyAsync(ws->d_mult, h_mult + k0, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+                staged_copy = true;
                 rc = launch(false, ws->d_keys, ws->d_mult, n, SmallQuery{});
                 if (rc) return rc;
             }
@@ -908,8 +1022,10 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
         TVZ_CUDA(cudaMemsetAsync(d_out, 0, 8, st));
         TVZ_CUDA(cudaMemsetAsync(ws->d_nhits, 0, 8, st));
     }
-    TVZ_CUDA(cudaEventRecord(ws->staged, st));
-    ws->stage_busy = true;
+    if (staged_copy) {
+        TVZ_CUDA(cudaEventRecord(ws->staged, st));
+        ws->stage_busy = true;
+    }
     return TVZ_OK;
 }
 
