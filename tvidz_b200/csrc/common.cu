@@ -1,5 +1,6 @@
 // Error reporting and device queries shared by the C-ABI entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -16,6 +17,14 @@ int set_error(int code, const char *fmt, ...) {
     vsnprintf(err_buf(), 512, fmt, ap);
     va_end(ap);
     return code;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("TVZ_NO_PDL");
+        return !(e && e[0] == '1');
+    }();
+    return on;
 }
 
 int num_sms() {

@@ -90,6 +90,31 @@ int guarded(F &&body) noexcept {
         if (!(cond)) return tvz::set_error(TVZ_ERR_INVALID, __VA_ARGS__);                     \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ----
+// The kernels of one query (count -> compaction [-> next query's count]) are launched with the
+// programmatic-stream-serialization attribute: a kernel's CTAs may become resident and run their
+// prologue (first loads, shared-memory tables) while the predecessor's last CTAs drain, and block
+// in pdl_wait() until the predecessor has completed and flushed -- which takes the grid launch
+// latency off the critical path of a 50 us query.  Every such kernel calls pdl_launch_dependents()
+// at its top and pdl_wait() before it touches anything its predecessor writes (on all paths).
+bool pdl_enabled();  // common.cu: off with TVZ_NO_PDL=1
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- mbarrier / TMA bulk-copy PTX wrappers (shared::cta addresses as u32) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -137,6 +137,8 @@ fragment_match_kernel(const int *__restrict__ ticks, const long long *__restrict
                       const __grid_constant__ FragQuery fq, int shift, int *__restrict__ score_out,
                       int *__restrict__ delta_out) {
     __shared__ FragSmem sm;
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qn = fq.qn, tol = fq.tol, tol_gap = fq.tol_gap;
     const int ng = qn > 0 ? qn - 1 : 0;  // query intervals
@@ -392,6 +394,7 @@ fragment_stream_kernel(const int *__restrict__ ticks, long long n_vals, long lon
                        int l2_ahead, int queue_cap) {
     static_assert(A >= 2 && A <= kMaxAnchor, "anchor length");
     __shared__ StreamSmem sm;
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qn = fq.qn;
     const int ng = qn - 1;                      // query intervals (>= A, checked by the host)
@@ -407,6 +410,7 @@ fragment_stream_kernel(const int *__restrict__ ticks, long long n_vals, long lon
         for (long long b = lo; b <= hi; ++b) atomicOr(&sm.table[b & (kMaxBuckets - 1)], 1u << (i & 31));
     }
     __syncthreads();
+    pdl_wait();  // keys[] is being read and zeroed by the previous query's compaction until here
 
     const StreamCtx cx{ticks, off, block_row, keys, sm.q, sm.qpos[warp], sm.qset[warp], n_vals, qn, fq.tol, fq.tol_gap,
                        fq.min_match};
@@ -613,15 +617,9 @@ int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int t
                 return e ? atoi(e) : 0;  // measured: 0.115 ms without, 0.121 ms with (distance 1..4)
             }();
             const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, static_cast<long long>(kStreamMinBlocks) * num_sms())));
-            if (anchor == 2)
-                fragment_stream_kernel<2><<<grid, kStreamThreads, 0, st>>>(c->d_ticks, c->n_vals, c->n_padded, c->d_off,
-                                                                          c->d_block_row, c->n_rows, fq, shift, c->d_keys,
-                                                                          l2_ahead, queue_cap);
-            else
-                fragment_stream_kernel<3><<<grid, kStreamThreads, 0, st>>>(c->d_ticks, c->n_vals, c->n_padded, c->d_off,
-                                                                          c->d_block_row, c->n_rows, fq, shift, c->d_keys,
-                                                                          l2_ahead, queue_cap);
-            TVZ_CUDA(cudaGetLastError());
+            auto kern = anchor == 2 ? fragment_stream_kernel<2> : fragment_stream_kernel<3>;
+            TVZ_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), 0, st, c->d_ticks, c->n_vals, c->n_padded, c->d_off,
+                                c->d_block_row, c->n_rows, fq, shift, c->d_keys, l2_ahead, queue_cap));
         }
         return compact_enqueue_keys(c->d_keys, c->n_rows, min_match, c->d_vid, d_out, c->d_rows, out_cap, c->d_nhits,
                                     c->d_state, c->d_ticket, d_out + 2 * (out_cap + 1), st);

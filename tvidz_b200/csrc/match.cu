@@ -28,15 +28,20 @@ namespace tvz {
 namespace {
 
 constexpr int kMapEntries = 1 << 16;         // byte-map filter of the query: 64 KB of shared memory
-constexpr int kMaxKeys = 2048;               // distinct query values per launch
+#ifndef TVZ_MAX_KEYS
+#define TVZ_MAX_KEYS 2048
+#endif
+constexpr int kMaxKeys = TVZ_MAX_KEYS;       // distinct query values per launch
 constexpr int kCountThreads = 512;            // batched kernel (streams the 8-byte values)
 constexpr int kCountUnroll = 8;               // 8 x 16 B (= 4 x 256-bit loads) in flight per thread
 constexpr int kChunkPairs = kCountThreads * kCountUnroll;  // 4096 pairs = 8192 values per CTA iteration
 constexpr int kCountWarps = kCountThreads / 32;
 constexpr int kWarpQueue = 64;               // filter survivors parked per warp
 constexpr int kBlockShift = 7;               // coarse row index: one entry per 128 stored values
-constexpr int kScanThreads = 256;
-constexpr int kScanRowsPerThread = 8;
+// 8192 rows per block: the look-back walks its predecessors 32 at a time, and every hop is a dependent
+// global round trip -- 1 M rows are 123 blocks (<= 4 hops) instead of 489 (<= 15 hops, ~8 us)
+constexpr int kScanThreads = 512;
+constexpr int kScanRowsPerThread = 16;
 constexpr int kScanRowsPerBlock = kScanThreads * kScanRowsPerThread;
 constexpr unsigned long long kPadPattern = 0x7ff8dead0000beefull;  // a NaN: never equals a stored value
 
@@ -108,7 +113,13 @@ constexpr int kFpThreads = TVZ_FP_THREADS;
 constexpr int kFpWarps = kFpThreads / 32;
 constexpr int kFpUnits = TVZ_FP_UNITS;       // 256-bit loads in flight per thread
 constexpr int kFpPerUnit = 32 * 16;          // fingerprints per warp-wide load
-constexpr int kFpQueue = 128;                // survivors parked per warp
+#ifndef TVZ_FP_QUEUE
+#define TVZ_FP_QUEUE 128
+#endif
+#ifndef TVZ_FP_MINB
+#define TVZ_FP_MINB (TVZ_FP_THREADS >= 1024 ? 1 : 2)
+#endif
+constexpr int kFpQueue = TVZ_FP_QUEUE;       // survivors parked per warp
 
 struct alignas(16) FpSmem {
     unsigned char map[kMapEntries];   // first: zeroed with 16-byte stores
@@ -190,7 +201,7 @@ __device__ __noinline__ void fp_drain(const FpCtx &cx, const FpSmem &sm, const l
 }
 
 template <bool kParamQuery>
-__global__ void __launch_bounds__(kFpThreads, kFpThreads >= 1024 ? 1 : 2)
+__global__ void __launch_bounds__(kFpThreads, TVZ_FP_MINB)
 match_count_kernel(const unsigned short *__restrict__ fp, long long n_units, const unsigned long long *__restrict__ ts,
                    long long n_vals, const unsigned long long *__restrict__ keys, const int *__restrict__ mult,
                    int n_keys, const long long *__restrict__ off, const int *__restrict__ block_row, long long n_rows,
@@ -198,6 +209,7 @@ match_count_kernel(const unsigned short *__restrict__ fp, long long n_units, con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FpSmem &sm = *reinterpret_cast<FpSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_launch_dependents();
     // the first loads do not depend on the query: issue them before the byte map is built
     const long long n_warps = static_cast<long long>(gridDim.x) * kFpWarps;
     const long long wg = static_cast<long long>(blockIdx.x) * kFpWarps + warp;
@@ -218,6 +230,7 @@ match_count_kernel(const unsigned short *__restrict__ fp, long long n_units, con
         sm.map[filter_hash(k)] = 1;
     }
     __syncthreads();
+    pdl_wait();  // counts[] is being read and zeroed by the previous query's compaction until here
 
     const FpCtx cx{ts, off, block_row, counts, n_vals, n_rows, n_keys};
     long long *qe = sm.qe[warp];
@@ -295,6 +308,8 @@ match_count_batch_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_p
                          long long counts_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BatchSmem &sm = *reinterpret_cast<BatchSmem *>(smem_raw);
+    pdl_launch_dependents();
+    pdl_wait();  // keys / n_keys are uploaded, counts[] zeroed by what runs before
     for (int i = threadIdx.x; i < kMapEntries / 16; i += kCountThreads)
         reinterpret_cast<uint4 *>(sm.map)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x < kBatch) sm.n_keys[threadIdx.x] = threadIdx.x < n_batch ? n_keys[threadIdx.x] : 0;
@@ -419,6 +434,8 @@ match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, 
                      long long *__restrict__ n_hits_out, unsigned long long *state, unsigned *ticket,
                      const int *__restrict__ aux, int *__restrict__ aux_out, const __grid_constant__ GatherTargets gt,
                      const BatchStrides bs, unsigned long long *__restrict__ keys) {
+    pdl_launch_dependents();
+    pdl_wait();  // the count / fragment kernel before this one must have finished
     // batched queries: blockIdx.y picks the query, everything below is per query
     counts += blockIdx.y * bs.counts;
     out += blockIdx.y * bs.out;
@@ -446,18 +463,39 @@ match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, 
     int cnt[kScanRowsPerThread];
     int dec[kKeys ? kScanRowsPerThread : 1];
     int mine = 0;
+    // the thread's 16 rows in 128-bit loads (the arrays are cudaMalloc-aligned, r0 is a multiple of 16);
+    // the last, partial thread range of a shard goes row by row
+    const bool whole = r0 + kScanRowsPerThread <= n_rows;
+    int cin[kKeys ? 1 : kScanRowsPerThread];
+    unsigned long long kin[kKeys ? kScanRowsPerThread : 1];
+    if (whole) {
+        if (kKeys) {
+#pragma unroll
+            for (int j = 0; j < kScanRowsPerThread; j += 2) {
+                const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(keys + r0 + j);
+                kin[j] = t.x;
+                kin[j + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kScanRowsPerThread; j += 4) {
+                const int4 t = *reinterpret_cast<const int4 *>(counts + r0 + j);
+                cin[j] = t.x; cin[j + 1] = t.y; cin[j + 2] = t.z; cin[j + 3] = t.w;
+            }
+        }
+    }
 #pragma unroll
     for (int j = 0; j < kScanRowsPerThread; ++j) {
         cnt[j] = -1;
-        if (r0 + j < n_rows) {
+        if (whole || r0 + j < n_rows) {
             int c;
             if (kKeys) {
-                const unsigned long long k = keys[r0 + j];
+                const unsigned long long k = whole ? kin[j] : keys[r0 + j];
                 if (k != 0) keys[r0 + j] = 0;
                 c = frag_key_score(k);
                 dec[j] = frag_key_delta(k);
             } else {
-                c = counts[r0 + j];
+                c = whole ? cin[j] : counts[r0 + j];
                 if (c != 0) counts[r0 + j] = 0;
             }
             if (c >= min_match) { cnt[j] = c; ++mine; }
@@ -621,10 +659,9 @@ int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid
                     long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket,
                     const int *aux, int *aux_out, cudaStream_t st, const GatherTargets *gather) {
     const GatherTargets none{};
-    match_compact_kernel<false><<<compact_blocks(n_rows), kScanThreads, 0, st>>>(
-        counts, n_rows, min_match, vid, out, rows_out, cap, n_hits_out, state, ticket, aux, aux_out,
-        gather ? *gather : none, BatchStrides{}, nullptr);
-    TVZ_CUDA(cudaGetLastError());
+    TVZ_CUDA(launch_pdl(match_compact_kernel<false>, dim3(compact_blocks(n_rows)), dim3(kScanThreads), 0, st, counts,
+                        n_rows, min_match, vid, out, rows_out, cap, n_hits_out, state, ticket, aux, aux_out,
+                        gather ? *gather : none, BatchStrides{}, static_cast<unsigned long long *>(nullptr)));
     return TVZ_OK;
 }
 
@@ -632,10 +669,9 @@ int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid
 int compact_enqueue_keys(unsigned long long *keys, long long n_rows, int min_match, const int *vid, int *out,
                          long long *rows_out, long long cap, long long *n_hits_out, unsigned long long *state,
                          unsigned *ticket, int *delta_out, cudaStream_t st) {
-    match_compact_kernel<true><<<compact_blocks(n_rows), kScanThreads, 0, st>>>(
-        nullptr, n_rows, min_match, vid, out, rows_out, cap, n_hits_out, state, ticket, nullptr, delta_out,
-        GatherTargets{}, BatchStrides{}, keys);
-    TVZ_CUDA(cudaGetLastError());
+    TVZ_CUDA(launch_pdl(match_compact_kernel<true>, dim3(compact_blocks(n_rows)), dim3(kScanThreads), 0, st,
+                        static_cast<int *>(nullptr), n_rows, min_match, vid, out, rows_out, cap, n_hits_out, state, ticket,
+                        static_cast<const int *>(nullptr), delta_out, GatherTargets{}, BatchStrides{}, keys));
     return TVZ_OK;
 }
 
@@ -644,10 +680,9 @@ int compact_enqueue_batch(int *counts, long long n_rows, int min_match, const in
                           const BatchStrides &bs, cudaStream_t st) {
     const GatherTargets none{};
     dim3 grid(compact_blocks(n_rows), n_batch);
-    match_compact_kernel<false><<<grid, kScanThreads, 0, st>>>(counts, n_rows, min_match, vid, out, rows_out, cap,
-                                                               n_hits_out, state, ticket, nullptr, nullptr, none, bs,
-                                                               nullptr);
-    TVZ_CUDA(cudaGetLastError());
+    TVZ_CUDA(launch_pdl(match_compact_kernel<false>, grid, dim3(kScanThreads), 0, st, counts, n_rows, min_match, vid, out,
+                        rows_out, cap, n_hits_out, state, ticket, static_cast<const int *>(nullptr),
+                        static_cast<int *>(nullptr), none, bs, static_cast<unsigned long long *>(nullptr)));
     return TVZ_OK;
 }
 
@@ -978,15 +1013,14 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
     if (cat->n_rows > 0) {
         const int sms = num_sms();
         const long long want = (cat->n_units + kFpWarps - 1) / kFpWarps;   // at least one unit per warp
-        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, 2ll * sms)));
+        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(TVZ_FP_MINB) * sms)));
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
         auto launch = [&](bool param, const unsigned long long *dk, const int *dm, int n, const SmallQuery &sq) -> int {
             auto kern = param ? match_count_kernel<true> : match_count_kernel<false>;
             TVZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(sizeof(FpSmem))));
-            kern<<<grid, kFpThreads, sizeof(FpSmem), st>>>(cat->d_fp, cat->n_units, cat->d_ts, cat->n_vals, dk, dm, n,
-                                                           cat->d_off, cat->d_block_row, cat->n_rows, ws->d_counts, sq);
-            TVZ_CUDA(cudaGetLastError());
+            TVZ_CUDA(launch_pdl(kern, dim3(grid), dim3(kFpThreads), sizeof(FpSmem), st, cat->d_fp, cat->n_units, cat->d_ts,
+                                cat->n_vals, dk, dm, n, cat->d_off, cat->d_block_row, cat->n_rows, ws->d_counts, sq));
             return TVZ_OK;
         };
         if (nk <= kParamKeys) {
