@@ -376,13 +376,39 @@ def run_ours(args):
             enqueue()
         m1.record(stream)
         barrier()
-        m_ms = max_over_ranks(m0.elapsed_time(m1)) / Km
+        m_ms_b2b = max_over_ranks(m0.elapsed_time(m1)) / Km          # back to back: L2 may keep part of the shard
+        # `value`: every query starts with a cold L2 -- a 256 MB buffer is rewritten and read back in between
+        # (the read leaves clean lines, so the query does not also pay for the flush's write-backs); the
+        # fingerprint array of the 1M-row catalogue (128 MB) would otherwise partly survive in the 126 MB L2
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        sink = torch.zeros(1, dtype=torch.int64, device=dev)
+        qev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Km)]
+        barrier()
+        for a, b in qev:
+            flush.zero_()
+            sink += flush.view(torch.int64).sum()
+            a.record(stream)
+            enqueue()
+            b.record(stream)
+        barrier()
+        m_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in qev])))
+        del flush, sink
         barrier()
         t0 = time.perf_counter()
         for _ in range(Km):
             full()
         torch.cuda.synchronize()
         m_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / Km
+        # the reference's default threshold (db.py:76 min_match=5): one hit instead of ~19k chance hits, so the
+        # Python list of tuples that dominates the figure above is short
+        full5 = (lambda: cat.find_duplicates(q, 5)) if world == 1 else (lambda: sc.find_duplicates(q, 5))
+        hits5 = full5()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Km):
+            full5()
+        torch.cuda.synchronize()
+        m_e2e5 = max_over_ranks((time.perf_counter() - t0) * 1e3) / Km
         # the dominant kernel alone, bracketed by CUDA events on its own stream inside the library
         local_cat.debug_count_kernel_ms(True)
         kms = []
@@ -391,9 +417,11 @@ def run_ours(args):
             kms.append(local_cat.debug_count_kernel_ms())
         local_cat.debug_count_kernel_ms(False)
         count_ms = max_over_ranks(float(np.mean(kms)))
-        algo_total = 8 * int(off[-1]) + 8 * (CATALOGUE_ROWS + 1)
+        streamed = 2 * n_values                                      # the count kernel streams 16-bit fingerprints
         matching = {"metric": "video-pair matches/s", "value": CATALOGUE_ROWS / (m_ms * 1e-3), "unit": "pairs/s",
-                    "ms_per_query": m_ms, "scaling": "strong", "n_gpus": world,
+                    "ms_per_query": m_ms, "ms_per_query_back_to_back": m_ms_b2b,
+                    "l2": "flushed before every timed query (256 MB rewritten, then read); back_to_back = no flush, queries "
+                          "pipelined on the stream", "scaling": "strong", "n_gpus": world,
                     "config": {"workload": "configs[3]: one full-duplicate query against 1M synthetic "
                                            "cut-timestamp arrays, rows sharded over the GPUs",
                                "rows": CATALOGUE_ROWS, "values": int(off[-1]), "query_len": int(len(q)),
@@ -407,17 +435,28 @@ def run_ours(args):
                     "e2e": {"value": CATALOGUE_ROWS / (m_e2e * 1e-3), "unit": "pairs/s", "ms_per_query": m_e2e,
                             "h2d_bytes_per_step": int(len(q) * 8 * 2 + len(q) * 4),
                             "d2h_bytes_per_step": int((len(hits) + 1) * 8),
-                            "path": "Catalogue.find_duplicates: host query in, Python list of tuples out"},
+                            "path": "Catalogue.find_duplicates: host query in, Python list of tuples out",
+                            "min_match_5": {"value": CATALOGUE_ROWS / (m_e2e5 * 1e-3), "unit": "pairs/s",
+                                            "ms_per_query": m_e2e5, "hits": len(hits5)}},
                     "roofline": {"bound": "hbm", "achieved": local_algo / (count_ms * 1e-3) / 1e9,
                                  "peak": peak_gbs, "unit": "GB/s",
                                  "frac": local_algo / (count_ms * 1e-3) / 1e9 / peak_gbs,
                                  "traffic": ncu_traffic("match_count_kernel") if world == 1 else None,
-                                 "kernel": "match_count_kernel", "kernel_ms": count_ms,
+                                 "kernel": "match_count_kernel (streams 16-bit fingerprints of the stored values)",
+                                 "kernel_ms": count_ms,
                                  "algorithmic_bytes_per_launch": int(local_algo),
+                                 "streamed_bytes_per_launch": int(streamed),
+                                 "achieved_streamed_bytes": streamed / (count_ms * 1e-3) / 1e9,
+                                 "frac_streamed_bytes": streamed / (count_ms * 1e-3) / 1e9 / peak_gbs,
                                  "note": "per GPU (slowest rank); algorithmic bytes 8*values + 8*(rows+1) of "
-                                         "the local shard per SURVEY.md 8d; ms_per_query above is the whole "
-                                         "query (upload + count + scan + emit"
-                                         + (" + all_gather)" if world > 1 else ")"),
+                                         "the local shard per SURVEY.md 8d, which asks for this accounting even "
+                                         "when a narrower lossless encoding is stored: the kernel reads 2 B per "
+                                         "stored value (its filter_hash) and verifies survivors against the 8-byte "
+                                         "values, so frac > 1 means less traffic than the accounting assumes, not "
+                                         "more than the HBM can deliver; the kernel is bound by its one "
+                                         "shared-memory lookup per value; ms_per_query above is the whole "
+                                         "query (count + compaction"
+                                         + (" + gather)" if world > 1 else ")"),
                                  "peak_source": peak_src},
                     "gpu_launches_per_query": 3}
         if world > 1 and not args.no_weak:

@@ -244,3 +244,27 @@ def test_batched_queries_equal_single_queries(cuda, match_golden):
         got = cat.find_duplicates_many([c["query"]] * 3 + [[]], mm)
         assert [list(x) for x in got[0]] == c["expected"] and got[0] == got[1] == got[2]
         cat.close()
+
+
+def test_pipelined_async_queries_keep_their_own_results(cuda):
+    """Different queries enqueued back to back on one stream (no host wait in between; the kernels
+    overlap their neighbours' tails through programmatic dependent launch) each fill their own
+    record with exactly the oracle's hit list -- including dense queries that drain the survivor
+    queue mid-stream and queries too long for the kernel parameters."""
+    import torch
+    ts, off, vid = synth.synth_catalogue(150_000, seed=21)
+    cat = Catalogue(ts, off, vid, hit_capacity=1 << 15)
+    rng = np.random.default_rng(21)
+    dense = np.unique(ts[rng.integers(0, ts.shape[0], 1500)])           # ~1500 keys: two-copy upload path
+    queries = [ts[off[r]:off[r + 1]] for r in (5, 77_000, 149_999)] + [dense, np.zeros(0), ts[off[9]:off[10]]]
+    queries = queries * 3
+    recs = [torch.zeros(((1 << 15) + 1, 2), dtype=torch.int32, device="cuda") for _ in queries]
+    for q, rec in zip(queries, recs):
+        cat.match_async(q, 2, rec)
+    torch.cuda.synchronize()
+    for q, rec in zip(queries, recs):
+        r = rec.cpu().numpy()
+        n = int(r[0, 0])
+        assert r[0, 1] == 0
+        assert [tuple(x) for x in r[1:1 + n].tolist()] == oracle.find_duplicates_csr(ts, off, vid, q, 2)
+    cat.close()

@@ -95,8 +95,9 @@ int guarded(F &&body) noexcept {
 // programmatic-stream-serialization attribute: a kernel's CTAs may become resident and run their
 // prologue (first loads, shared-memory tables) while the predecessor's last CTAs drain, and block
 // in pdl_wait() until the predecessor has completed and flushed -- which takes the grid launch
-// latency off the critical path of a 50 us query.  Every such kernel calls pdl_launch_dependents()
-// at its top and pdl_wait() before it touches anything its predecessor writes (on all paths).
+// latency off the critical path of a 50 us query.  Every such kernel calls pdl_wait() before it
+// touches anything its predecessor writes (on all paths) and pdl_launch_dependents() right after,
+// so a kernel two places down the stream never starts before the kernel two places up has finished.
 bool pdl_enabled();  // common.cu: off with TVZ_NO_PDL=1
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

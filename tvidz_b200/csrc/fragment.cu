@@ -137,8 +137,8 @@ fragment_match_kernel(const int *__restrict__ ticks, const long long *__restrict
                       const __grid_constant__ FragQuery fq, int shift, int *__restrict__ score_out,
                       int *__restrict__ delta_out) {
     __shared__ FragSmem sm;
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qn = fq.qn, tol = fq.tol, tol_gap = fq.tol_gap;
     const int ng = qn > 0 ? qn - 1 : 0;  // query intervals
@@ -394,7 +394,6 @@ fragment_stream_kernel(const int *__restrict__ ticks, long long n_vals, long lon
                        int l2_ahead, int queue_cap) {
     static_assert(A >= 2 && A <= kMaxAnchor, "anchor length");
     __shared__ StreamSmem sm;
-    pdl_launch_dependents();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qn = fq.qn;
     const int ng = qn - 1;                      // query intervals (>= A, checked by the host)
@@ -411,6 +410,7 @@ fragment_stream_kernel(const int *__restrict__ ticks, long long n_vals, long lon
     }
     __syncthreads();
     pdl_wait();  // keys[] is being read and zeroed by the previous query's compaction until here
+    pdl_launch_dependents();
 
     const StreamCtx cx{ticks, off, block_row, keys, sm.q, sm.qpos[warp], sm.qset[warp], n_vals, qn, fq.tol, fq.tol_gap,
                        fq.min_match};

@@ -38,9 +38,9 @@ constexpr int kChunkPairs = kCountThreads * kCountUnroll;  // 4096 pairs = 8192 
 constexpr int kCountWarps = kCountThreads / 32;
 constexpr int kWarpQueue = 64;               // filter survivors parked per warp
 constexpr int kBlockShift = 7;               // coarse row index: one entry per 128 stored values
-// 8192 rows per block: the look-back walks its predecessors 32 at a time, and every hop is a dependent
-// global round trip -- 1 M rows are 123 blocks (<= 4 hops) instead of 489 (<= 15 hops, ~8 us)
-constexpr int kScanThreads = 512;
+// 16384 rows per block: the look-back walks its predecessors 32 at a time, and every hop is a dependent
+// global round trip -- 1 M rows are 62 blocks (<= 2 hops) instead of 489 (<= 15 hops, ~8 us)
+constexpr int kScanThreads = 1024;
 constexpr int kScanRowsPerThread = 16;
 constexpr int kScanRowsPerBlock = kScanThreads * kScanRowsPerThread;
 constexpr unsigned long long kPadPattern = 0x7ff8dead0000beefull;  // a NaN: never equals a stored value
@@ -209,7 +209,6 @@ match_count_kernel(const unsigned short *__restrict__ fp, long long n_units, con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FpSmem &sm = *reinterpret_cast<FpSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    pdl_launch_dependents();
     // the first loads do not depend on the query: issue them before the byte map is built
     const long long n_warps = static_cast<long long>(gridDim.x) * kFpWarps;
     const long long wg = static_cast<long long>(blockIdx.x) * kFpWarps + warp;
@@ -231,6 +230,7 @@ match_count_kernel(const unsigned short *__restrict__ fp, long long n_units, con
     }
     __syncthreads();
     pdl_wait();  // counts[] is being read and zeroed by the previous query's compaction until here
+    pdl_launch_dependents();  // only now: this query's compaction takes its tickets before ITS wait
 
     const FpCtx cx{ts, off, block_row, counts, n_vals, n_rows, n_keys};
     long long *qe = sm.qe[warp];
@@ -308,8 +308,8 @@ match_count_batch_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_p
                          long long counts_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BatchSmem &sm = *reinterpret_cast<BatchSmem *>(smem_raw);
-    pdl_launch_dependents();
     pdl_wait();  // keys / n_keys are uploaded, counts[] zeroed by what runs before
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < kMapEntries / 16; i += kCountThreads)
         reinterpret_cast<uint4 *>(sm.map)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x < kBatch) sm.n_keys[threadIdx.x] = threadIdx.x < n_batch ? n_keys[threadIdx.x] : 0;
@@ -434,8 +434,6 @@ match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, 
                      long long *__restrict__ n_hits_out, unsigned long long *state, unsigned *ticket,
                      const int *__restrict__ aux, int *__restrict__ aux_out, const __grid_constant__ GatherTargets gt,
                      const BatchStrides bs, unsigned long long *__restrict__ keys) {
-    pdl_launch_dependents();
-    pdl_wait();  // the count / fragment kernel before this one must have finished
     // batched queries: blockIdx.y picks the query, everything below is per query
     counts += blockIdx.y * bs.counts;
     out += blockIdx.y * bs.out;
@@ -449,12 +447,17 @@ match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, 
     __shared__ unsigned s_block, s_epoch;
     __shared__ long long s_excl;
     __shared__ int ws[kScanThreads / 32];
+    // Tickets are taken BEFORE the dependency wait: ticket and epoch are only ever touched by compaction
+    // kernels, and the previous one has completed (the kernel in between waited for it before it let
+    // this one launch), so these two global round trips hide behind the count kernel's tail.
     if (threadIdx.x == 0) {
         unsigned e;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(ticket + 1) : "memory");
         s_epoch = e;
         s_block = atomicAdd(ticket, 1u);
     }
+    pdl_launch_dependents();
+    pdl_wait();  // the count / fragment kernel before this one must have finished
     __syncthreads();
     const unsigned blk = s_block;
     const unsigned epoch = s_epoch;
