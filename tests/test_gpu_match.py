@@ -253,12 +253,12 @@ def test_pipelined_async_queries_keep_their_own_results(cuda):
     queue mid-stream and queries too long for the kernel parameters."""
     import torch
     ts, off, vid = synth.synth_catalogue(150_000, seed=21)
-    cat = Catalogue(ts, off, vid, hit_capacity=1 << 15)
+    cat = Catalogue(ts, off, vid, hit_capacity=1 << 17)
     rng = np.random.default_rng(21)
-    dense = np.unique(ts[rng.integers(0, ts.shape[0], 1500)])           # ~1500 keys: two-copy upload path
+    dense = np.unique(ts[rng.integers(0, ts.shape[0], 1500)])           # ~1500 keys, 115k hit rows: upload path
     queries = [ts[off[r]:off[r + 1]] for r in (5, 77_000, 149_999)] + [dense, np.zeros(0), ts[off[9]:off[10]]]
     queries = queries * 3
-    recs = [torch.zeros(((1 << 15) + 1, 2), dtype=torch.int32, device="cuda") for _ in queries]
+    recs = [torch.zeros(((1 << 17) + 1, 2), dtype=torch.int32, device="cuda") for _ in queries]
     for q, rec in zip(queries, recs):
         cat.match_async(q, 2, rec)
     torch.cuda.synchronize()
