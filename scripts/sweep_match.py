@@ -11,12 +11,9 @@ sys.path.insert(0, ROOT)
 VAR_DIR = os.path.join(ROOT, "build", "variants")
 VARIANTS = {            # name: (threads, units, extra defines)
     "fp_t512_u2": (512, 2, []),
+    "fp_t512_u3": (512, 3, []),
+    "fp_t512_u4": (512, 4, []),
     "fp_t768_b2_u2": (768, 2, ["-DTVZ_FP_MINB=2", "-DTVZ_FP_QUEUE=96"]),
-    "fp_t768_b2_u1": (768, 1, ["-DTVZ_FP_MINB=2", "-DTVZ_FP_QUEUE=96"]),
-    "fp_t1024_b2_u2": (1024, 2, ["-DTVZ_FP_MINB=2", "-DTVZ_FP_QUEUE=64", "-DTVZ_MAX_KEYS=512"]),
-    "fp_t1024_b2_u1": (1024, 1, ["-DTVZ_FP_MINB=2", "-DTVZ_FP_QUEUE=64", "-DTVZ_MAX_KEYS=512"]),
-    "fp_t512_b3_u2": (512, 2, ["-DTVZ_FP_MINB=3", "-DTVZ_FP_QUEUE=64", "-DTVZ_MAX_KEYS=256"]),
-    "fp_t256_b4_u2": (256, 2, ["-DTVZ_FP_MINB=4", "-DTVZ_FP_QUEUE=128"]),
 }
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     from tvidz_b200 import build as b

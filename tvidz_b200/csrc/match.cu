@@ -146,46 +146,25 @@ __device__ __forceinline__ U32x8 ld_stream_u32x8(const void *p) {
 
 // What a survivor needs to be verified.
 struct FpCtx {
-    const unsigned long long *ts;
-    const long long *off;
-    const int *block_row;
+    const unsigned long long *rec_ts;  // value behind the fingerprint at an arranged position
+    const unsigned *rec_row;           // and its row
     int *counts;
-    long long n_vals, n_rows;
     int n_keys;
 };
 
-// Verify one survivor: the value and the coarse row index are fetched together (both depend only
-// on the element index), the sorted query keys are searched in shared memory, and the row is picked
-// from four consecutive offsets loaded at once (a 256-value block rarely spans more rows; the
-// general case falls back to a binary search).  Three dependent memory round trips per survivor.
-__device__ __forceinline__ void fp_resolve(const FpCtx &cx, const FpSmem &sm, long long elem) {
-    if (elem >= cx.n_vals) return;  // padding
-    const unsigned long long v = __ldg(cx.ts + elem);
-    const long long b = elem >> kBlockShift;
-    long long a = __ldg(cx.block_row + b);
-    const long long z = __ldg(cx.block_row + b + 1) + 1;  // last row with off[row] <= elem is in [a, z)
+// Verify one survivor: ONE memory round trip (value and row of the arranged position, fetched together
+// and already on their way to L2 since the survivor was parked), then the sorted query keys are
+// searched in shared memory and a real match adds into counts[row].
+__device__ __forceinline__ void fp_resolve(const FpCtx &cx, const FpSmem &sm, long long pos) {
+    const unsigned long long v = __ldg(cx.rec_ts + pos);
+    const unsigned row = __ldg(cx.rec_row + pos);
     int lo = 0, hi = cx.n_keys;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (sm.keys[mid] < v) lo = mid + 1; else hi = mid;
     }
-    if (lo >= cx.n_keys || sm.keys[lo] != v) return;  // fingerprint collision
-    if (z - a <= 5) {
-        long long o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = __ldg(cx.off + min(a + 1 + k, cx.n_rows));
-        int step = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) step += (a + 1 + k < z) && (o[k] <= elem);  // off is non-decreasing
-        a += step;
-    } else {
-        long long zz = z;
-        while (zz - a > 1) {
-            const long long mid = (a + zz) >> 1;
-            if (__ldg(cx.off + mid) <= elem) a = mid; else zz = mid;
-        }
-    }
-    atomicAdd(&cx.counts[a], sm.mult[lo]);
+    if (lo >= cx.n_keys || sm.keys[lo] != v) return;  // fingerprint collision (or padding)
+    atomicAdd(&cx.counts[row], sm.mult[lo]);
 }
 
 // Verify the warp's parked survivors, 32 at a time (called by the whole warp).  Out of line for the
@@ -202,9 +181,9 @@ __device__ __noinline__ void fp_drain(const FpCtx &cx, const FpSmem &sm, const l
 
 template <bool kParamQuery>
 __global__ void __launch_bounds__(kFpThreads, TVZ_FP_MINB)
-match_count_kernel(const unsigned short *__restrict__ fp, long long n_units, const unsigned long long *__restrict__ ts,
-                   long long n_vals, const unsigned long long *__restrict__ keys, const int *__restrict__ mult,
-                   int n_keys, const long long *__restrict__ off, const int *__restrict__ block_row, long long n_rows,
+match_count_kernel(const unsigned short *__restrict__ fp, long long n_units,
+                   const unsigned long long *__restrict__ rec_ts, const unsigned *__restrict__ rec_row,
+                   const unsigned long long *__restrict__ keys, const int *__restrict__ mult, int n_keys,
                    int *__restrict__ counts, const __grid_constant__ SmallQuery sq) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FpSmem &sm = *reinterpret_cast<FpSmem *>(smem_raw);
@@ -232,7 +211,7 @@ match_count_kernel(const unsigned short *__restrict__ fp, long long n_units, con
     pdl_wait();  // counts[] is being read and zeroed by the previous query's compaction until here
     pdl_launch_dependents();  // only now: this query's compaction takes its tickets before ITS wait
 
-    const FpCtx cx{ts, off, block_row, counts, n_vals, n_rows, n_keys};
+    const FpCtx cx{rec_ts, rec_row, counts, n_keys};
     long long *qe = sm.qe[warp];
     int queued = 0;  // warp-uniform, <= kFpQueue
 
@@ -270,9 +249,9 @@ match_count_kernel(const unsigned short *__restrict__ fp, long long n_units, con
                         const long long e = e0 + (__ffs(flags) - 1);
                         qe[queued + __popc(mask & ((1u << lane) - 1u))] = e;
                         flags &= flags - 1;
-                        // what the verification will read first, on its way to L2 while the stream goes on
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ts + e));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(block_row + (e >> kBlockShift)));
+                        // what the verification will read, on its way to L2 while the stream goes on
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec_ts + e));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec_row + e));
                     }
                     queued += __popc(mask);
                     mask = __ballot_sync(0xffffffffu, flags != 0u);
@@ -704,7 +683,10 @@ struct tvz_catalog {
     long long n_rows = 0, n_vals = 0, n_pairs = 0;
     long long n_pairs_padded = 0;  // ts is padded with a NaN pattern to whole count-kernel chunks
     unsigned long long *d_ts = nullptr;
-    unsigned short *d_fp = nullptr;  // filter_hash of every stored value, padded to whole 512-value units
+    unsigned short *d_fp = nullptr;  // filter_hash of every stored value, padded to whole 512-value units and
+                                     // arranged inside each unit for conflict-free lookups (arrange_fingerprints)
+    unsigned long long *d_rec_ts = nullptr;  // the value behind d_fp[p], in the same arranged order ...
+    unsigned *d_rec_row = nullptr;           // ... and the row it belongs to: what a surviving fingerprint is checked against
     long long n_units = 0;
     long long *d_off = nullptr;
     int *d_vid = nullptr;
@@ -755,6 +737,52 @@ inline unsigned long long canon_bits(double v) {
 }
 inline bool is_nan_bits(unsigned long long b) {
     return (b & 0x7ff0000000000000ull) == 0x7ff0000000000000ull && (b & 0x000fffffffffffffull) != 0;
+}
+
+// Fingerprints of one 512-value unit, ARRANGED so that the k-th lookups of the 32 lanes (positions
+// lane * 16 + k, k = 0..15) fall into 32 different shared-memory banks wherever the unit allows it.
+// The byte-map lookup of fingerprint f goes to bank (f >> 2) & 31 whatever the query is, so this is
+// decided once, when the catalogue is packed: the values of each bank are dealt one per round k;
+// banks that hold more than 16 of the unit's 512 values (about a tenth of them do not fit) fill the
+// holes the short banks leave in the last rounds.  Random placement costs 3.6 wavefronts per LDS.U8,
+// this ~1.3.  perm[] maps an arranged position back to the value's offset inside the unit (it is read
+// for survivors only).
+void arrange_fingerprints(const unsigned long long *ts, long long n_vals, long long n_units, unsigned short *fp,
+                          unsigned short *perm) {
+    std::vector<unsigned short> bank_items[32];
+    std::vector<unsigned short> overflow;
+    for (long long u = 0; u < std::max<long long>(1, n_units); ++u) {
+        const long long base = u * kFpPerUnit;
+        unsigned short f[kFpPerUnit];
+        for (int i = 0; i < kFpPerUnit; ++i)
+            f[i] = base + i < n_vals ? static_cast<unsigned short>(filter_hash(ts[base + i])) : 0;
+        for (auto &b : bank_items) b.clear();
+        overflow.clear();
+        for (int i = 0; i < kFpPerUnit; ++i) bank_items[(f[i] >> 2) & 31].push_back(static_cast<unsigned short>(i));
+        int fill[16];  // lanes used in round k
+        unsigned short round_items[16][32];
+        for (int k = 0; k < 16; ++k) fill[k] = 0;
+        for (int b = 0; b < 32; ++b) {
+            for (size_t j = 0; j < bank_items[b].size(); ++j) {
+                if (j < 16) round_items[j][fill[j]++] = bank_items[b][j];
+                else overflow.push_back(bank_items[b][j]);
+            }
+        }
+        // overflow goes to the rounds with holes, spread so that one bank's extras land in different rounds
+        int k = 15;
+        for (unsigned short item : overflow) {
+            int tries = 0;
+            while (fill[k] >= 32 && tries < 16) { k = (k + 15) % 16; ++tries; }
+            round_items[k][fill[k]++] = item;
+            k = (k + 15) % 16;
+        }
+        for (int r = 0; r < 16; ++r)
+            for (int lane = 0; lane < 32; ++lane) {
+                const unsigned short i = round_items[r][lane];
+                fp[base + lane * 16 + r] = f[i];
+                perm[base + lane * 16 + r] = i;
+            }
+    }
 }
 
 int ensure_query_capacity(tvz_match_ws *ws, int qn) {
@@ -837,7 +865,31 @@ int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *
     // 16-bit fingerprints, padded to whole warp units (pad entries point past n_vals and are dropped)
     c->n_units = (c->n_vals + kFpPerUnit - 1) / kFpPerUnit;
     std::vector<unsigned short> fp(static_cast<size_t>(std::max<long long>(1, c->n_units)) * kFpPerUnit, 0);
-    for (long long i = 0; i < c->n_vals; ++i) fp[i] = static_cast<unsigned short>(filter_hash(ts[i]));
+    std::vector<unsigned short> perm(fp.size(), 0);
+    arrange_fingerprints(ts.data(), c->n_vals, c->n_units, fp.data(), perm.data());
+    // verification records in ARRANGED order: a surviving fingerprint at position p is checked against
+    // rec_ts[p] and, if it is a real match, adds into counts[rec_row[p]] -- one memory round trip, no
+    // search for the row.  Pad positions hold a NaN pattern that equals no query key.
+    std::vector<unsigned long long> rec_ts(fp.size(), kPadPattern);
+    std::vector<unsigned> rec_row(fp.size(), 0u);
+    {
+        std::vector<unsigned> row_of(kFpPerUnit);
+        long long r = 0;
+        for (long long u = 0; u < c->n_units; ++u) {
+            const long long base = u * kFpPerUnit;
+            for (int i = 0; i < kFpPerUnit && base + i < c->n_vals; ++i) {
+                while (r + 1 < n_rows && off[r + 1] <= base + i) ++r;
+                row_of[i] = static_cast<unsigned>(r);
+            }
+            for (int p2 = 0; p2 < kFpPerUnit; ++p2) {
+                const long long elem = base + perm[base + p2];
+                if (elem < c->n_vals) {
+                    rec_ts[base + p2] = ts[elem];
+                    rec_row[base + p2] = row_of[perm[base + p2]];
+                }
+            }
+        }
+    }
     cudaGetDevice(&c->device);
     auto fail = [&](cudaError_t e, const char *what) {
         set_error(TVZ_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
@@ -849,6 +901,12 @@ int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *
     if ((e = cudaMalloc(&c->d_fp, fp.size() * 2)) != cudaSuccess) return fail(e, "cudaMalloc(fp)");
     if ((e = cudaMemcpy(c->d_fp, fp.data(), fp.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail(e, "cudaMemcpy(fp)");
+    if ((e = cudaMalloc(&c->d_rec_ts, rec_ts.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(rec_ts)");
+    if ((e = cudaMemcpy(c->d_rec_ts, rec_ts.data(), rec_ts.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(rec_ts)");
+    if ((e = cudaMalloc(&c->d_rec_row, rec_row.size() * 4)) != cudaSuccess) return fail(e, "cudaMalloc(rec_row)");
+    if ((e = cudaMemcpy(c->d_rec_row, rec_row.data(), rec_row.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(rec_row)");
     if ((e = cudaMalloc(&c->d_off, off.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(off)");
     if ((e = cudaMalloc(&c->d_vid, std::max<size_t>(1, n_rows) * 4)) != cudaSuccess) return fail(e, "cudaMalloc(vid)");
     if ((e = cudaMalloc(&c->d_block_row, block_row.size() * 4)) != cudaSuccess) return fail(e, "cudaMalloc(block_row)");
@@ -870,6 +928,8 @@ void tvz_catalog_destroy(tvz_catalog *c) {
     if (!c) return;
     if (c->d_ts) cudaFree(c->d_ts);
     if (c->d_fp) cudaFree(c->d_fp);
+    if (c->d_rec_ts) cudaFree(c->d_rec_ts);
+    if (c->d_rec_row) cudaFree(c->d_rec_row);
     if (c->d_off) cudaFree(c->d_off);
     if (c->d_vid) cudaFree(c->d_vid);
     if (c->d_block_row) cudaFree(c->d_block_row);
@@ -1022,8 +1082,8 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
             auto kern = param ? match_count_kernel<true> : match_count_kernel<false>;
             TVZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(sizeof(FpSmem))));
-            TVZ_CUDA(launch_pdl(kern, dim3(grid), dim3(kFpThreads), sizeof(FpSmem), st, cat->d_fp, cat->n_units, cat->d_ts,
-                                cat->n_vals, dk, dm, n, cat->d_off, cat->d_block_row, cat->n_rows, ws->d_counts, sq));
+            TVZ_CUDA(launch_pdl(kern, dim3(grid), dim3(kFpThreads), sizeof(FpSmem), st, cat->d_fp, cat->n_units, cat->d_rec_ts,
+                                cat->d_rec_row, dk, dm, n, ws->d_counts, sq));
             return TVZ_OK;
         };
         if (nk <= kParamKeys) {
