@@ -442,7 +442,8 @@ def run_ours(args):
                                  "peak": peak_gbs, "unit": "GB/s",
                                  "frac": local_algo / (count_ms * 1e-3) / 1e9 / peak_gbs,
                                  "traffic": ncu_traffic("match_count_kernel") if world == 1 else None,
-                                 "kernel": "match_count_kernel (streams 16-bit fingerprints of the stored values)",
+                                 "kernel": "match_count_kernel (streams 16-bit fingerprints of the stored values; "
+                                           "the ordered compaction runs in the same cooperative launch)",
                                  "kernel_ms": count_ms,
                                  "algorithmic_bytes_per_launch": int(local_algo),
                                  "streamed_bytes_per_launch": int(streamed),
@@ -453,12 +454,12 @@ def run_ours(args):
                                          "when a narrower lossless encoding is stored: the kernel reads 2 B per "
                                          "stored value (its filter_hash) and verifies survivors against the 8-byte "
                                          "values, so frac > 1 means less traffic than the accounting assumes, not "
-                                         "more than the HBM can deliver; the kernel is bound by its one "
-                                         "shared-memory lookup per value; ms_per_query above is the whole "
-                                         "query (count + compaction"
-                                         + (" + gather)" if world > 1 else ")"),
+                                         "more than the HBM can deliver; kernel_ms is the whole fused launch "
+                                         "(count + compaction"
+                                         + (" + peer stores of the hit record; the wait kernel behind it is in "
+                                            "ms_per_query)" if world > 1 else ")"),
                                  "peak_source": peak_src},
-                    "gpu_launches_per_query": 3}
+                    "gpu_launches_per_query": 1 if world == 1 else 2}
         if world > 1 and not args.no_weak:
             # weak-scaling companion: 1M rows PER GPU (rank r holds rows r*1M.. of a world*1M-row catalogue)
             wts, woff, wvid = synth.synth_catalogue(CATALOGUE_ROWS, seed=1000 + rank)

@@ -618,7 +618,7 @@ int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int t
             }();
             const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, static_cast<long long>(kStreamMinBlocks) * num_sms())));
             auto kern = anchor == 2 ? fragment_stream_kernel<2> : fragment_stream_kernel<3>;
-            TVZ_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), 0, st, c->d_ticks, c->n_vals, c->n_padded, c->d_off,
+            TVZ_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), 0, st, false, c->d_ticks, c->n_vals, c->n_padded, c->d_off,
                                 c->d_block_row, c->n_rows, fq, shift, c->d_keys, l2_ahead, queue_cap));
         }
         return compact_enqueue_keys(c->d_keys, c->n_rows, min_match, c->d_vid, d_out, c->d_rows, out_cap, c->d_nhits,

@@ -18,6 +18,8 @@
 // the query rejects ~all values with one LDS.U8, and the rare survivors are looked up exactly
 // and added to counts[row] with a RED.  One query streams the 2-byte fingerprints (`fp`) and
 // touches `ts` only for survivors; the batched kernel (8 queries per pass) streams `ts` itself.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <unordered_set>
 #include <vector>
@@ -179,12 +181,145 @@ __device__ __noinline__ void fp_drain(const FpCtx &cx, const FpSmem &sm, const l
     fp_drain_inline(cx, sm, qe, n);
 }
 
+// Fused compaction (single launch for a whole query): after the last survivor has been verified the
+// grid synchronises (cooperative launch: all CTAs are resident), every CTA counts the qualifying rows
+// of its 4096-row chunks, the grid synchronises again, and every CTA writes its chunks' rows behind
+// the hits of all earlier chunks -- the same ordered record as match_compact_kernel, without a second
+// launch, its cold start and the ticket / look-back protocol.  counts[] is zeroed on the way.
+constexpr int kFusedRowsPerThread = 8;
+constexpr int kFusedChunk = kFpThreads * kFusedRowsPerThread;
+struct FusedCompact {
+    int enabled = 0;
+    int min_match = 0;
+    long long n_rows = 0, cap = 0;
+    const int *vid = nullptr;
+    int *out = nullptr;
+    long long *rows_out = nullptr;
+    long long *n_hits_out = nullptr;
+    unsigned *chunk_hits = nullptr;  // [n_chunks]
+    unsigned *done = nullptr;        // fused gather: CTAs finished
+    GatherTargets gt;
+};
+
+__device__ __forceinline__ void fused_compact(const FusedCompact &fc, int *__restrict__ counts, int *ws32) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long n_chunks = (fc.n_rows + kFusedChunk - 1) / kFusedChunk;
+    __shared__ long long s_excl;
+    auto load8 = [&](long long r0, int (&c)[kFusedRowsPerThread]) {
+        if (r0 + kFusedRowsPerThread <= fc.n_rows) {
+            const int4 a = *reinterpret_cast<const int4 *>(counts + r0);
+            const int4 b = *reinterpret_cast<const int4 *>(counts + r0 + 4);
+            c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < kFusedRowsPerThread; ++j) c[j] = r0 + j < fc.n_rows ? counts[r0 + j] : 0;
+        }
+    };
+    grid.sync();  // every count of this query is final
+    // pass A: hits per chunk
+    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        int c[kFusedRowsPerThread];
+        load8(ch * kFusedChunk + threadIdx.x * kFusedRowsPerThread, c);
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < kFusedRowsPerThread; ++j) mine += c[j] >= fc.min_match && ch * kFusedChunk + threadIdx.x * kFusedRowsPerThread + j < fc.n_rows;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        __syncthreads();
+        if (lane == 0) ws32[warp] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned t = 0;
+            for (int w = 0; w < kFpWarps; ++w) t += ws32[w];
+            fc.chunk_hits[ch] = t;
+        }
+    }
+    grid.sync();  // every chunk's hit count is published
+    // pass B: ordered emission
+    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        __syncthreads();
+        if (warp == 0) {  // hits of all earlier chunks
+            long long e = 0;
+            for (long long i = lane; i < ch; i += 32) e += fc.chunk_hits[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            if (lane == 0) s_excl = e;
+        }
+        const long long r0 = ch * kFusedChunk + threadIdx.x * kFusedRowsPerThread;
+        int c[kFusedRowsPerThread];
+        load8(r0, c);
+        int mine = 0;  // counts are never negative: -1 marks "does not qualify / no such row"
+#pragma unroll
+        for (int j = 0; j < kFusedRowsPerThread; ++j) {
+            if (r0 + j < fc.n_rows) {
+                if (c[j] != 0) counts[r0 + j] = 0;
+                if (c[j] >= fc.min_match) ++mine; else c[j] = -1;
+            } else {
+                c[j] = -1;
+            }
+        }
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) ws32[warp] = incl;
+        __syncthreads();
+        int wofs = 0;
+        for (int w = 0; w < warp; ++w) wofs += ws32[w];
+        long long pos = s_excl + wofs + (incl - mine);
+#pragma unroll
+        for (int j = 0; j < kFusedRowsPerThread; ++j) {
+            if (c[j] >= 0) {
+                if (pos < fc.cap) {
+                    const int v = fc.vid[r0 + j];
+                    fc.out[2 + 2 * pos] = v;
+                    fc.out[3 + 2 * pos] = c[j];
+                    fc.rows_out[pos] = r0 + j;
+                    for (int p2 = 0; p2 < fc.gt.n_peers; ++p2)
+                        *reinterpret_cast<int2 *>(fc.gt.record[p2] + 2 + 2 * pos) = make_int2(v, c[j]);
+                }
+                ++pos;
+            }
+        }
+        if (ch == n_chunks - 1 && threadIdx.x == kFpThreads - 1) {  // the last thread of the last chunk knows the total
+            const long long total = pos;
+            *fc.n_hits_out = total;
+            fc.out[0] = total > 0x7fffffffll ? 0x7fffffff : static_cast<int>(total);
+            fc.out[1] = total > fc.cap ? 1 : 0;
+        }
+    }
+    if (fc.gt.n_peers == 0) return;
+    // fused gather epilogue: the CTA that finishes last publishes the header and the flag on every peer
+    __shared__ unsigned s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned d = atomicAdd(fc.done, 1u);
+        s_last = d == gridDim.x - 1;
+        if (s_last) *fc.done = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x < fc.gt.n_peers) {
+        __threadfence_system();
+        const int2 hdr = make_int2(*reinterpret_cast<volatile int *>(fc.out), *reinterpret_cast<volatile int *>(fc.out + 1));
+        *reinterpret_cast<int2 *>(fc.gt.record[threadIdx.x]) = hdr;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fc.gt.flag[threadIdx.x]), "r"(fc.gt.epoch) : "memory");
+    }
+}
+
 template <bool kParamQuery>
 __global__ void __launch_bounds__(kFpThreads, TVZ_FP_MINB)
 match_count_kernel(const unsigned short *__restrict__ fp, long long n_units,
                    const unsigned long long *__restrict__ rec_ts, const unsigned *__restrict__ rec_row,
                    const unsigned long long *__restrict__ keys, const int *__restrict__ mult, int n_keys,
-                   int *__restrict__ counts, const __grid_constant__ SmallQuery sq) {
+                   int *__restrict__ counts, const __grid_constant__ SmallQuery sq,
+                   const __grid_constant__ FusedCompact fc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FpSmem &sm = *reinterpret_cast<FpSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -262,6 +397,7 @@ match_count_kernel(const unsigned short *__restrict__ fp, long long n_units,
         }
     }
     fp_drain_inline(cx, sm, qe, queued);
+    if (fc.enabled) fused_compact(fc, counts, sm.mult);  // (the mult table is dead by now: scratch for the scans)
 }
 
 // ---- batched queries: up to 8 find_duplicates calls answered by ONE pass over the catalogue ----
@@ -641,7 +777,7 @@ int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid
                     long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket,
                     const int *aux, int *aux_out, cudaStream_t st, const GatherTargets *gather) {
     const GatherTargets none{};
-    TVZ_CUDA(launch_pdl(match_compact_kernel<false>, dim3(compact_blocks(n_rows)), dim3(kScanThreads), 0, st, counts,
+    TVZ_CUDA(launch_pdl(match_compact_kernel<false>, dim3(compact_blocks(n_rows)), dim3(kScanThreads), 0, st, false, counts,
                         n_rows, min_match, vid, out, rows_out, cap, n_hits_out, state, ticket, aux, aux_out,
                         gather ? *gather : none, BatchStrides{}, static_cast<unsigned long long *>(nullptr)));
     return TVZ_OK;
@@ -651,7 +787,7 @@ int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid
 int compact_enqueue_keys(unsigned long long *keys, long long n_rows, int min_match, const int *vid, int *out,
                          long long *rows_out, long long cap, long long *n_hits_out, unsigned long long *state,
                          unsigned *ticket, int *delta_out, cudaStream_t st) {
-    TVZ_CUDA(launch_pdl(match_compact_kernel<true>, dim3(compact_blocks(n_rows)), dim3(kScanThreads), 0, st,
+    TVZ_CUDA(launch_pdl(match_compact_kernel<true>, dim3(compact_blocks(n_rows)), dim3(kScanThreads), 0, st, false,
                         static_cast<int *>(nullptr), n_rows, min_match, vid, out, rows_out, cap, n_hits_out, state, ticket,
                         static_cast<const int *>(nullptr), delta_out, GatherTargets{}, BatchStrides{}, keys));
     return TVZ_OK;
@@ -662,7 +798,7 @@ int compact_enqueue_batch(int *counts, long long n_rows, int min_match, const in
                           const BatchStrides &bs, cudaStream_t st) {
     const GatherTargets none{};
     dim3 grid(compact_blocks(n_rows), n_batch);
-    TVZ_CUDA(launch_pdl(match_compact_kernel<false>, grid, dim3(kScanThreads), 0, st, counts, n_rows, min_match, vid, out,
+    TVZ_CUDA(launch_pdl(match_compact_kernel<false>, grid, dim3(kScanThreads), 0, st, false, counts, n_rows, min_match, vid, out,
                         rows_out, cap, n_hits_out, state, ticket, static_cast<const int *>(nullptr),
                         static_cast<int *>(nullptr), none, bs, static_cast<unsigned long long *>(nullptr)));
     return TVZ_OK;
@@ -704,6 +840,7 @@ struct tvz_match_ws {
     long long *d_rows = nullptr;   // [cap]
     int *d_kth = nullptr;          // [cap]
     long long *d_nhits = nullptr;  // [1]
+    unsigned *d_chunk_hits = nullptr;  // [n_rows / 4096 + 1] fused compaction: qualifying rows per chunk
     // query staging: keys u64 [kMaxKeys] | q_canon u64 [q_cap] | mult i32 [kMaxKeys]
     unsigned long long *d_keys = nullptr, *d_qcanon = nullptr;
     int *d_mult = nullptr;
@@ -971,6 +1108,8 @@ int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_
     if ((e = cudaMalloc(&ws->d_rows, ws->cap * 8)) != cudaSuccess) return bail(e, "cudaMalloc(rows)");
     if ((e = cudaMalloc(&ws->d_kth, ws->cap * 4)) != cudaSuccess) return bail(e, "cudaMalloc(kth)");
     if ((e = cudaMalloc(&ws->d_nhits, 8)) != cudaSuccess) return bail(e, "cudaMalloc(nhits)");
+    if ((e = cudaMalloc(&ws->d_chunk_hits, (nr / kFusedChunk + 2) * 4)) != cudaSuccess)
+        return bail(e, "cudaMalloc(chunk_hits)");
     if ((e = cudaMemset(ws->d_nhits, 0, 8)) != cudaSuccess) return bail(e, "cudaMemset(nhits)");
     if ((e = cudaMalloc(&ws->d_keys, kMaxKeys * 8)) != cudaSuccess) return bail(e, "cudaMalloc(keys)");
     if ((e = cudaMalloc(&ws->d_mult, kMaxKeys * 4)) != cudaSuccess) return bail(e, "cudaMalloc(mult)");
@@ -1001,6 +1140,7 @@ void tvz_match_ws_destroy(tvz_match_ws *ws) {
     if (ws->d_rows) cudaFree(ws->d_rows);
     if (ws->d_kth) cudaFree(ws->d_kth);
     if (ws->d_nhits) cudaFree(ws->d_nhits);
+    if (ws->d_chunk_hits) cudaFree(ws->d_chunk_hits);
     if (ws->d_keys) cudaFree(ws->d_keys);
     if (ws->d_mult) cudaFree(ws->d_mult);
     if (ws->d_qcanon) cudaFree(ws->d_qcanon);
@@ -1078,12 +1218,33 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
         const long long want = (cat->n_units + kFpWarps - 1) / kFpWarps;   // at least one unit per warp
         const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(TVZ_FP_MINB) * sms)));
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
+        // One launch for the whole query when the keys fit one count launch: the kernel compacts its own
+        // counts behind two grid-wide barriers (cooperative launch).  TVZ_NO_FUSE=1 keeps the two kernels.
+        static const bool fuse_ok = [] {
+            const char *e = getenv("TVZ_NO_FUSE");
+            return !(e && e[0] == '1');
+        }();
+        const bool fused = fuse_ok && nk > 0 && nk <= kMaxKeys;
+        FusedCompact fc;
+        if (fused) {
+            fc.enabled = 1;
+            fc.min_match = min_match;
+            fc.n_rows = cat->n_rows;
+            fc.cap = out_cap;
+            fc.vid = cat->d_vid;
+            fc.out = d_out;
+            fc.rows_out = ws->d_rows;
+            fc.n_hits_out = ws->d_nhits;
+            fc.chunk_hits = ws->d_chunk_hits;
+            fc.done = ws->d_ticket + 2;
+            if (gather) fc.gt = *gather;
+        }
         auto launch = [&](bool param, const unsigned long long *dk, const int *dm, int n, const SmallQuery &sq) -> int {
             auto kern = param ? match_count_kernel<true> : match_count_kernel<false>;
             TVZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(sizeof(FpSmem))));
-            TVZ_CUDA(launch_pdl(kern, dim3(grid), dim3(kFpThreads), sizeof(FpSmem), st, cat->d_fp, cat->n_units, cat->d_rec_ts,
-                                cat->d_rec_row, dk, dm, n, ws->d_counts, sq));
+            TVZ_CUDA(launch_pdl(kern, dim3(fused ? 2 * sms : grid), dim3(kFpThreads), sizeof(FpSmem), st, fused, cat->d_fp,
+                                cat->n_units, cat->d_rec_ts, cat->d_rec_row, dk, dm, n, ws->d_counts, sq, fc));
             return TVZ_OK;
         };
         if (nk <= kParamKeys) {
@@ -1106,9 +1267,11 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
             }
         }
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
-        rc = compact_enqueue(ws->d_counts, cat->n_rows, min_match, cat->d_vid, d_out, ws->d_rows, out_cap, ws->d_nhits,
-                             ws->d_state, ws->d_ticket, nullptr, nullptr, st, gather);
-        if (rc) return rc;
+        if (!fused) {
+            rc = compact_enqueue(ws->d_counts, cat->n_rows, min_match, cat->d_vid, d_out, ws->d_rows, out_cap,
+                                 ws->d_nhits, ws->d_state, ws->d_ticket, nullptr, nullptr, st, gather);
+            if (rc) return rc;
+        }
         if (want_kth) {
             match_kth_kernel<<<2 * sms, 256, 0, st>>>(cat->d_ts, cat->d_off, ws->d_rows, d_out, out_cap,
                                                       ws->d_qcanon, qn, min_match, ws->d_kth);
