@@ -146,10 +146,14 @@ __device__ __forceinline__ U32x8 ld_stream_u32x8(const void *p) {
     return r;
 }
 
-// What a survivor needs to be verified.
+// What a surviving fingerprint is checked against: the value behind it and the row it belongs to, one
+// 16-byte record per arranged position (one DRAM fetch per survivor).
+struct alignas(16) VerifyRec {
+    unsigned long long ts;
+    unsigned row, pad;
+};
 struct FpCtx {
-    const unsigned long long *rec_ts;  // value behind the fingerprint at an arranged position
-    const unsigned *rec_row;           // and its row
+    const VerifyRec *rec;
     int *counts;
     int n_keys;
 };
@@ -158,8 +162,9 @@ struct FpCtx {
 // and already on their way to L2 since the survivor was parked), then the sorted query keys are
 // searched in shared memory and a real match adds into counts[row].
 __device__ __forceinline__ void fp_resolve(const FpCtx &cx, const FpSmem &sm, long long pos) {
-    const unsigned long long v = __ldg(cx.rec_ts + pos);
-    const unsigned row = __ldg(cx.rec_row + pos);
+    const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(cx.rec + pos));
+    const unsigned long long v = (static_cast<unsigned long long>(r4.y) << 32) | r4.x;
+    const unsigned row = r4.z;
     int lo = 0, hi = cx.n_keys;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -316,7 +321,7 @@ __device__ __forceinline__ void fused_compact(const FusedCompact &fc, int *__res
 template <bool kParamQuery>
 __global__ void __launch_bounds__(kFpThreads, TVZ_FP_MINB)
 match_count_kernel(const unsigned short *__restrict__ fp, long long n_units,
-                   const unsigned long long *__restrict__ rec_ts, const unsigned *__restrict__ rec_row,
+                   const VerifyRec *__restrict__ rec,
                    const unsigned long long *__restrict__ keys, const int *__restrict__ mult, int n_keys,
                    int *__restrict__ counts, const __grid_constant__ SmallQuery sq,
                    const __grid_constant__ FusedCompact fc) {
@@ -346,7 +351,7 @@ match_count_kernel(const unsigned short *__restrict__ fp, long long n_units,
     pdl_wait();  // counts[] is being read and zeroed by the previous query's compaction until here
     pdl_launch_dependents();  // only now: this query's compaction takes its tickets before ITS wait
 
-    const FpCtx cx{rec_ts, rec_row, counts, n_keys};
+    const FpCtx cx{rec, counts, n_keys};
     long long *qe = sm.qe[warp];
     int queued = 0;  // warp-uniform, <= kFpQueue
 
@@ -385,8 +390,7 @@ match_count_kernel(const unsigned short *__restrict__ fp, long long n_units,
                         qe[queued + __popc(mask & ((1u << lane) - 1u))] = e;
                         flags &= flags - 1;
                         // what the verification will read, on its way to L2 while the stream goes on
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec_ts + e));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec_row + e));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + e));
                     }
                     queued += __popc(mask);
                     mask = __ballot_sync(0xffffffffu, flags != 0u);
@@ -821,8 +825,7 @@ struct tvz_catalog {
     unsigned long long *d_ts = nullptr;
     unsigned short *d_fp = nullptr;  // filter_hash of every stored value, padded to whole 512-value units and
                                      // arranged inside each unit for conflict-free lookups (arrange_fingerprints)
-    unsigned long long *d_rec_ts = nullptr;  // the value behind d_fp[p], in the same arranged order ...
-    unsigned *d_rec_row = nullptr;           // ... and the row it belongs to: what a surviving fingerprint is checked against
+    void *d_rec = nullptr;           // VerifyRec[p]: the value behind d_fp[p] and its row, in the same arranged order
     long long n_units = 0;
     long long *d_off = nullptr;
     int *d_vid = nullptr;
@@ -1005,10 +1008,9 @@ int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *
     std::vector<unsigned short> perm(fp.size(), 0);
     arrange_fingerprints(ts.data(), c->n_vals, c->n_units, fp.data(), perm.data());
     // verification records in ARRANGED order: a surviving fingerprint at position p is checked against
-    // rec_ts[p] and, if it is a real match, adds into counts[rec_row[p]] -- one memory round trip, no
-    // search for the row.  Pad positions hold a NaN pattern that equals no query key.
-    std::vector<unsigned long long> rec_ts(fp.size(), kPadPattern);
-    std::vector<unsigned> rec_row(fp.size(), 0u);
+    // rec[p].ts and, if it is a real match, adds into counts[rec[p].row] -- one 16-byte load, no search
+    // for the row.  Pad positions hold a NaN pattern that equals no query key.
+    std::vector<VerifyRec> rec(fp.size(), VerifyRec{kPadPattern, 0u, 0u});
     {
         std::vector<unsigned> row_of(kFpPerUnit);
         long long r = 0;
@@ -1021,8 +1023,8 @@ int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *
             for (int p2 = 0; p2 < kFpPerUnit; ++p2) {
                 const long long elem = base + perm[base + p2];
                 if (elem < c->n_vals) {
-                    rec_ts[base + p2] = ts[elem];
-                    rec_row[base + p2] = row_of[perm[base + p2]];
+                    rec[base + p2].ts = ts[elem];
+                    rec[base + p2].row = row_of[perm[base + p2]];
                 }
             }
         }
@@ -1038,12 +1040,9 @@ int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *
     if ((e = cudaMalloc(&c->d_fp, fp.size() * 2)) != cudaSuccess) return fail(e, "cudaMalloc(fp)");
     if ((e = cudaMemcpy(c->d_fp, fp.data(), fp.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail(e, "cudaMemcpy(fp)");
-    if ((e = cudaMalloc(&c->d_rec_ts, rec_ts.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(rec_ts)");
-    if ((e = cudaMemcpy(c->d_rec_ts, rec_ts.data(), rec_ts.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
-        return fail(e, "cudaMemcpy(rec_ts)");
-    if ((e = cudaMalloc(&c->d_rec_row, rec_row.size() * 4)) != cudaSuccess) return fail(e, "cudaMalloc(rec_row)");
-    if ((e = cudaMemcpy(c->d_rec_row, rec_row.data(), rec_row.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
-        return fail(e, "cudaMemcpy(rec_row)");
+    if ((e = cudaMalloc(&c->d_rec, rec.size() * sizeof(VerifyRec))) != cudaSuccess) return fail(e, "cudaMalloc(rec)");
+    if ((e = cudaMemcpy(c->d_rec, rec.data(), rec.size() * sizeof(VerifyRec), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(rec)");
     if ((e = cudaMalloc(&c->d_off, off.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(off)");
     if ((e = cudaMalloc(&c->d_vid, std::max<size_t>(1, n_rows) * 4)) != cudaSuccess) return fail(e, "cudaMalloc(vid)");
     if ((e = cudaMalloc(&c->d_block_row, block_row.size() * 4)) != cudaSuccess) return fail(e, "cudaMalloc(block_row)");
@@ -1065,8 +1064,7 @@ void tvz_catalog_destroy(tvz_catalog *c) {
     if (!c) return;
     if (c->d_ts) cudaFree(c->d_ts);
     if (c->d_fp) cudaFree(c->d_fp);
-    if (c->d_rec_ts) cudaFree(c->d_rec_ts);
-    if (c->d_rec_row) cudaFree(c->d_rec_row);
+    if (c->d_rec) cudaFree(c->d_rec);
     if (c->d_off) cudaFree(c->d_off);
     if (c->d_vid) cudaFree(c->d_vid);
     if (c->d_block_row) cudaFree(c->d_block_row);
@@ -1244,7 +1242,7 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
             TVZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(sizeof(FpSmem))));
             TVZ_CUDA(launch_pdl(kern, dim3(fused ? 2 * sms : grid), dim3(kFpThreads), sizeof(FpSmem), st, fused, cat->d_fp,
-                                cat->n_units, cat->d_rec_ts, cat->d_rec_row, dk, dm, n, ws->d_counts, sq, fc));
+                                cat->n_units, cat->d_rec, dk, dm, n, ws->d_counts, sq, fc));
             return TVZ_OK;
         };
         if (nk <= kParamKeys) {
