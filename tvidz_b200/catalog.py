@@ -169,7 +169,7 @@ class Catalogue:
     def match_gather_async(self, new_timestamps, min_match: int, peer_record: np.ndarray, peer_flag: np.ndarray,
                            my_flags_ptr: int, out_cap: int, epoch: int, stream=None) -> None:
         """Enqueue one query whose per-shard record is stored straight into every peer's gather
-        buffer by the compaction kernel (tvz_catalog_match_gather_async)."""
+        buffer by the compaction phase of the query's kernel (tvz_catalog_match_gather_async)."""
         q = np.ascontiguousarray(np.asarray(new_timestamps, dtype=np.float64).reshape(-1))
         peer_record = np.ascontiguousarray(peer_record, np.uint64)
         peer_flag = np.ascontiguousarray(peer_flag, np.uint64)

@@ -59,7 +59,7 @@ class ShardedCatalogue:
     gloo tests inject a CPU stand-in to exercise this host logic).
 
     gather="nccl"  : one all_gather_into_tensor of the fixed-size records per query.
-    gather="fused" : the records live in symmetric (peer-mapped) memory and the compaction kernel
+    gather="fused" : the records live in symmetric (peer-mapped) memory and the query's kernel (its compaction phase)
                      itself stores each rank's record into every peer over NVLink and raises a
                      flag; no collective launch on the data path (tvz_catalog_match_gather_async).
     """
