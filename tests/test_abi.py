@@ -60,3 +60,32 @@ def test_product_never_imports_the_oracle():
                     src = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
                 assert "oracle/" not in src and "tvzo_" not in src, fn
+
+
+def test_fingerprint_layout_is_a_conflict_free_permutation():
+    """Host logic of the catalogue packer (no GPU): inside every 512-value unit the arranged
+    fingerprints are a permutation of the values' hashes, and the k-th lookups of the 32 lanes
+    (positions lane * 16 + k) fall into nearly 32 different shared-memory banks (banks that hold
+    more than 16 of a unit's values must double up somewhere)."""
+    import numpy as np
+    from tvidz_b200 import _lib, synth
+    ts, off, vid = synth.synth_catalogue(400, seed=5)
+    n = int(ts.shape[0])
+    padded = -(-n // 512) * 512
+    fp = np.zeros(padded, np.uint16)
+    perm = np.zeros(padded, np.uint16)
+    _lib.check(_lib.lib().tvz_debug_arrange_fingerprints(ts.ctypes.data, n, fp.ctypes.data, perm.ctypes.data))
+    bits = ts.view(np.uint64)
+    lo, hi = (bits & np.uint64(0xffffffff)).astype(np.uint64), (bits >> np.uint64(32)).astype(np.uint64)
+    h = (((lo * np.uint64(0x9E3779B1) + hi * np.uint64(0x85EBCA77)) & np.uint64(0xffffffff)) >> np.uint64(16)).astype(np.uint16)
+    worst = []
+    for u in range(padded // 512):
+        p = perm[u * 512:(u + 1) * 512].astype(np.int64)
+        assert sorted(p.tolist()) == list(range(512))                       # a permutation of the unit
+        idx = u * 512 + p
+        want = np.where(idx < n, h[np.minimum(idx, n - 1)], 0)
+        assert np.array_equal(fp[u * 512:(u + 1) * 512], want)             # every position carries its value's hash
+        if (u + 1) * 512 <= n:
+            banks = ((fp[u * 512:(u + 1) * 512] >> 2) & 31).reshape(32, 16)  # [lane][round]
+            worst.append(np.mean([np.bincount(banks[:, k], minlength=32).max() for k in range(16)]))
+    assert worst and np.mean(worst) < 2.1, np.mean(worst)                   # ~1.85; random placement gives ~3.6

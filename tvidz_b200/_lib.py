@@ -45,7 +45,8 @@ SYMBOLS = [
 # debug hooks outside the public header
 _DEBUG_SYMBOLS = [("tvz_debug_sad_tuning", _i, [_i, _i, _i, _i]),
                   ("tvz_debug_match_timing", _i, [_vp, _i]),
-                  ("tvz_debug_match_count_ms", _i, [_vp, C.POINTER(C.c_float)])]
+                  ("tvz_debug_match_count_ms", _i, [_vp, C.POINTER(C.c_float)]),
+                  ("tvz_debug_arrange_fingerprints", _i, [_vp, _i64, _vp, _vp])]
 
 TVZ_ERR_OVERFLOW = -4
 _lib = None

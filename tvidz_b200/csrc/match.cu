@@ -885,7 +885,7 @@ inline bool is_nan_bits(unsigned long long b) {
 // decided once, when the catalogue is packed: the values of each bank are dealt one per round k;
 // banks that hold more than 16 of the unit's 512 values (about a tenth of them do not fit) fill the
 // holes the short banks leave in the last rounds.  Random placement costs 3.6 wavefronts per LDS.U8,
-// this ~1.3.  perm[] maps an arranged position back to the value's offset inside the unit (it is read
+// this 1.85 (tests/test_abi.py).  perm[] maps an arranged position back to the value's offset inside the unit (it is read
 // for survivors only).
 void arrange_fingerprints(const unsigned long long *ts, long long n_vals, long long n_units, unsigned short *fp,
                           unsigned short *perm) {
@@ -1307,6 +1307,18 @@ int tvz_debug_match_count_ms(tvz_match_ws *ws, float *ms) {
     TVZ_CUDA(cudaEventSynchronize(ws->t1));
     TVZ_CUDA(cudaEventElapsedTime(ms, ws->t0, ws->t1));
     return TVZ_OK;
+}
+
+// Debug hook (host only, no GPU needed): the fingerprint layout of `n` stored values, as the catalogue
+// packer computes it.  fp_out / perm_out hold ceil(n / 512) * 512 entries.
+int tvz_debug_arrange_fingerprints(const double *values, int64_t n, uint16_t *fp_out, uint16_t *perm_out) {
+    return guarded([&]() -> int {
+    TVZ_REQUIRE(n >= 0 && (n == 0 || values) && fp_out && perm_out, "bad arguments");
+    std::vector<unsigned long long> bits(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) bits[i] = canon_bits(values[i]);
+    arrange_fingerprints(bits.data(), n, (n + kFpPerUnit - 1) / kFpPerUnit, fp_out, perm_out);
+    return TVZ_OK;
+    });
 }
 
 int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match,
