@@ -1222,7 +1222,7 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
             const char *e = getenv("TVZ_NO_FUSE");
             return !(e && e[0] == '1');
         }();
-        const bool fused = fuse_ok && nk > 0 && nk <= kMaxKeys;
+        bool fused = fuse_ok && nk > 0 && nk <= kMaxKeys;
         FusedCompact fc;
         if (fused) {
             fc.enabled = 1;
@@ -1241,8 +1241,17 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
             auto kern = param ? match_count_kernel<true> : match_count_kernel<false>;
             TVZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(sizeof(FpSmem))));
-            TVZ_CUDA(launch_pdl(kern, dim3(fused ? 2 * sms : grid), dim3(kFpThreads), sizeof(FpSmem), st, fused, cat->d_fp,
-                                cat->n_units, cat->d_rec, dk, dm, n, ws->d_counts, sq, fc));
+            cudaError_t le = launch_pdl(kern, dim3(fused ? 2 * sms : grid), dim3(kFpThreads), sizeof(FpSmem), st, fused,
+                                        cat->d_fp, cat->n_units, cat->d_rec, dk, dm, n, ws->d_counts, sq, fc);
+            if (le == cudaErrorCooperativeLaunchTooLarge && fused) {
+                // the device cannot hold 2 CTAs per SM right now (MPS limits, a debugger ...): two kernels
+                cudaGetLastError();
+                fused = false;
+                fc.enabled = 0;
+                le = launch_pdl(kern, dim3(grid), dim3(kFpThreads), sizeof(FpSmem), st, false, cat->d_fp, cat->n_units,
+                                cat->d_rec, dk, dm, n, ws->d_counts, sq, fc);
+            }
+            TVZ_CUDA(le);
             return TVZ_OK;
         };
         if (nk <= kParamKeys) {
