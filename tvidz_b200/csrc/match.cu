@@ -18,8 +18,6 @@
 // the query rejects ~all values with one LDS.U8, and the rare survivors are looked up exactly
 // and added to counts[row] with a RED.  One query streams the 2-byte fingerprints (`fp`) and
 // touches `ts` only for survivors; the batched kernel (8 queries per pass) streams `ts` itself.
-#include <cooperative_groups.h>
-
 #include <algorithm>
 #include <unordered_set>
 #include <vector>
@@ -186,137 +184,7 @@ __device__ __noinline__ void fp_drain(const FpCtx &cx, const FpSmem &sm, const l
     fp_drain_inline(cx, sm, qe, n);
 }
 
-// Fused compaction (single launch for a whole query): after the last survivor has been verified the
-// grid synchronises (cooperative launch: all CTAs are resident), every CTA counts the qualifying rows
-// of its 4096-row chunks, the grid synchronises again, and every CTA writes its chunks' rows behind
-// the hits of all earlier chunks -- the same ordered record as match_compact_kernel, without a second
-// launch, its cold start and the ticket / look-back protocol.  counts[] is zeroed on the way.
-constexpr int kFusedRowsPerThread = 8;
-constexpr int kFusedChunk = kFpThreads * kFusedRowsPerThread;
-struct FusedCompact {
-    int enabled = 0;
-    int min_match = 0;
-    long long n_rows = 0, cap = 0;
-    const int *vid = nullptr;
-    int *out = nullptr;
-    long long *rows_out = nullptr;
-    long long *n_hits_out = nullptr;
-    unsigned *chunk_hits = nullptr;  // [n_chunks]
-    unsigned *done = nullptr;        // fused gather: CTAs finished
-    GatherTargets gt;
-};
-
-__device__ __forceinline__ void fused_compact(const FusedCompact &fc, int *__restrict__ counts, int *ws32) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long n_chunks = (fc.n_rows + kFusedChunk - 1) / kFusedChunk;
-    __shared__ long long s_excl;
-    auto load8 = [&](long long r0, int (&c)[kFusedRowsPerThread]) {
-        if (r0 + kFusedRowsPerThread <= fc.n_rows) {
-            const int4 a = *reinterpret_cast<const int4 *>(counts + r0);
-            const int4 b = *reinterpret_cast<const int4 *>(counts + r0 + 4);
-            c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < kFusedRowsPerThread; ++j) c[j] = r0 + j < fc.n_rows ? counts[r0 + j] : 0;
-        }
-    };
-    grid.sync();  // every count of this query is final
-    // pass A: hits per chunk
-    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
-        int c[kFusedRowsPerThread];
-        load8(ch * kFusedChunk + threadIdx.x * kFusedRowsPerThread, c);
-        int mine = 0;
-#pragma unroll
-        for (int j = 0; j < kFusedRowsPerThread; ++j) mine += c[j] >= fc.min_match && ch * kFusedChunk + threadIdx.x * kFusedRowsPerThread + j < fc.n_rows;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-        __syncthreads();
-        if (lane == 0) ws32[warp] = mine;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned t = 0;
-            for (int w = 0; w < kFpWarps; ++w) t += ws32[w];
-            fc.chunk_hits[ch] = t;
-        }
-    }
-    grid.sync();  // every chunk's hit count is published
-    // pass B: ordered emission
-    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
-        __syncthreads();
-        if (warp == 0) {  // hits of all earlier chunks
-            long long e = 0;
-            for (long long i = lane; i < ch; i += 32) e += fc.chunk_hits[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-            if (lane == 0) s_excl = e;
-        }
-        const long long r0 = ch * kFusedChunk + threadIdx.x * kFusedRowsPerThread;
-        int c[kFusedRowsPerThread];
-        load8(r0, c);
-        int mine = 0;  // counts are never negative: -1 marks "does not qualify / no such row"
-#pragma unroll
-        for (int j = 0; j < kFusedRowsPerThread; ++j) {
-            if (r0 + j < fc.n_rows) {
-                if (c[j] != 0) counts[r0 + j] = 0;
-                if (c[j] >= fc.min_match) ++mine; else c[j] = -1;
-            } else {
-                c[j] = -1;
-            }
-        }
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        if (lane == 31) ws32[warp] = incl;
-        __syncthreads();
-        int wofs = 0;
-        for (int w = 0; w < warp; ++w) wofs += ws32[w];
-        long long pos = s_excl + wofs + (incl - mine);
-#pragma unroll
-        for (int j = 0; j < kFusedRowsPerThread; ++j) {
-            if (c[j] >= 0) {
-                if (pos < fc.cap) {
-                    const int v = fc.vid[r0 + j];
-                    fc.out[2 + 2 * pos] = v;
-                    fc.out[3 + 2 * pos] = c[j];
-                    fc.rows_out[pos] = r0 + j;
-                    for (int p2 = 0; p2 < fc.gt.n_peers; ++p2)
-                        *reinterpret_cast<int2 *>(fc.gt.record[p2] + 2 + 2 * pos) = make_int2(v, c[j]);
-                }
-                ++pos;
-            }
-        }
-        if (ch == n_chunks - 1 && threadIdx.x == kFpThreads - 1) {  // the last thread of the last chunk knows the total
-            const long long total = pos;
-            *fc.n_hits_out = total;
-            fc.out[0] = total > 0x7fffffffll ? 0x7fffffff : static_cast<int>(total);
-            fc.out[1] = total > fc.cap ? 1 : 0;
-        }
-    }
-    if (fc.gt.n_peers == 0) return;
-    // fused gather epilogue: the CTA that finishes last publishes the header and the flag on every peer
-    __shared__ unsigned s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const unsigned d = atomicAdd(fc.done, 1u);
-        s_last = d == gridDim.x - 1;
-        if (s_last) *fc.done = 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    if (threadIdx.x < fc.gt.n_peers) {
-        __threadfence_system();
-        const int2 hdr = make_int2(*reinterpret_cast<volatile int *>(fc.out), *reinterpret_cast<volatile int *>(fc.out + 1));
-        *reinterpret_cast<int2 *>(fc.gt.record[threadIdx.x]) = hdr;
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fc.gt.flag[threadIdx.x]), "r"(fc.gt.epoch) : "memory");
-    }
-}
+constexpr int kFusedChunk = kFpThreads * kFusedRowsPerThread;   // rows per chunk of the count kernel's fused compaction
 
 template <bool kParamQuery>
 __global__ void __launch_bounds__(kFpThreads, TVZ_FP_MINB)
@@ -401,7 +269,7 @@ match_count_kernel(const unsigned short *__restrict__ fp, long long n_units,
         }
     }
     fp_drain_inline(cx, sm, qe, queued);
-    if (fc.enabled) fused_compact(fc, counts, sm.mult);  // (the mult table is dead by now: scratch for the scans)
+    if (fc.enabled) fused_compact<kFpThreads, false>(fc, counts, sm.mult);  // (the mult table is dead by now: scratch)
 }
 
 // ---- batched queries: up to 8 find_duplicates calls answered by ONE pass over the catalogue ----
