@@ -100,7 +100,10 @@ typedef struct tvz_match_ws tvz_match_ws;   /* per-thread query workspace */
 /* Pack rows (CSR: h_ts[h_off[r] .. h_off[r+1]) is row r, h_video_id[r] its
  * videos.id) onto the current device.  Stored values are canonicalised so that
  * bitwise equality equals Python float `==` (db.py:88): -0.0 -> +0.0, NaNs
- * dropped, repeats inside a row dropped (they never change a match count). */
+ * dropped, repeats inside a row dropped (they never change a match count).
+ * Device memory: 26 bytes per stored value (the value in row order, a 16-bit
+ * fingerprint of it -- what a query streams -- and a 16-byte verification
+ * record) + 12 bytes per row. */
 int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_video_id,
                        int64_t n_rows, tvz_catalog **out);
 void tvz_catalog_destroy(tvz_catalog *cat);
@@ -135,8 +138,10 @@ int tvz_catalog_match_batch(const tvz_catalog *cat, tvz_match_ws *ws, const doub
                             int64_t *out_off, int64_t cap_total, int64_t *need_per_query, int64_t *need_total);
 
 /* Device-resident variant for pipelines, CUDA graphs and the sharded matcher:
- * enqueues the query upload, the count kernel and the ordered compaction on
- * `stream` and returns without synchronising.  The result is written to
+ * enqueues the query -- normally ONE cooperative kernel launch that counts and
+ * compacts (the keys of a query with <= 224 distinct values travel in the kernel
+ * parameters) -- on `stream` and returns without synchronising.  Back-to-back
+ * calls on one stream pipeline without a host-side wait.  The result is written to
  *   d_out : int32 [out_cap + 1][2] on the device (NULL = the workspace's own
  *           buffer, see tvz_match_ws_hits, capacity = hit_capacity):
  *             d_out[0]     = { n_hits saturated to INT32_MAX, 1 if n_hits > out_cap }
@@ -150,8 +155,8 @@ int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const doub
                             int min_match, int32_t *d_out, int64_t out_cap, void *stream);
 /* Sharded matcher with the gather fused into the kernel (one process per GPU, peers reachable
  * over NVLink): like tvz_catalog_match_async into the workspace's own record, but the
- * compaction's last block then STORES this rank's record ({n_hits, overflow} + hits) into
- * every peer's gather buffer and raises a per-rank flag there with a system-scope release;
+ * compaction phase also STORES this rank's record ({n_hits, overflow} + hits) into
+ * every peer's gather buffer and its last block raises a per-rank flag there with a system-scope release;
  * a one-warp kernel enqueued behind it waits until the flags of all peers show `epoch`.
  *   peer_record[p] : device address (peer memory) of THIS rank's slot, int32 [out_cap + 1][2],
  *                    inside peer p's gather buffer; peer_flag[p]: this rank's uint32 flag on peer p
