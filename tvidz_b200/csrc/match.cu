@@ -748,42 +748,45 @@ inline bool is_nan_bits(unsigned long long b) {
 }
 
 // Fingerprints of one 512-value unit, ARRANGED so that the k-th lookups of the 32 lanes (positions
-// lane * 16 + k, k = 0..15) fall into 32 different shared-memory banks wherever the unit allows it.
-// The byte-map lookup of fingerprint f goes to bank (f >> 2) & 31 whatever the query is, so this is
-// decided once, when the catalogue is packed: the values of each bank are dealt one per round k;
-// banks that hold more than 16 of the unit's 512 values (about a tenth of them do not fit) fill the
-// holes the short banks leave in the last rounds.  Random placement costs 3.6 wavefronts per LDS.U8,
-// this 1.85 (tests/test_abi.py).  perm[] maps an arranged position back to the value's offset inside the unit (it is read
-// for survivors only).
+// lane * 16 + k, k = 0..15: one "round") fall into 32 different shared-memory banks wherever the unit
+// allows it.  The byte-map lookup of fingerprint f goes to bank (f >> 2) & 31 whatever the query is,
+// so this is decided once, when the catalogue is packed.  A bank with exactly 16 of the unit's 512
+// values appears once in every round.  Banks with more (their extras) and banks with fewer (their
+// absences) are confined to the LAST T rounds, T = the largest surplus or deficit of any bank: extras
+// and absences are both dealt round-robin over those T rounds, so every round still holds exactly 32
+// values, the first 16 - T rounds are conflict-free and the last T are 2-way (random bank counts give
+// T ~ 8: 1.5 wavefronts per LDS.U8 instead of the 3.6 of an unordered unit; tests/test_abi.py).
+// perm[] maps an arranged position back to the value's offset inside the unit.
 void arrange_fingerprints(const unsigned long long *ts, long long n_vals, long long n_units, unsigned short *fp,
                           unsigned short *perm) {
     std::vector<unsigned short> bank_items[32];
-    std::vector<unsigned short> overflow;
     for (long long u = 0; u < std::max<long long>(1, n_units); ++u) {
         const long long base = u * kFpPerUnit;
         unsigned short f[kFpPerUnit];
         for (int i = 0; i < kFpPerUnit; ++i)
             f[i] = base + i < n_vals ? static_cast<unsigned short>(filter_hash(ts[base + i])) : 0;
         for (auto &b : bank_items) b.clear();
-        overflow.clear();
         for (int i = 0; i < kFpPerUnit; ++i) bank_items[(f[i] >> 2) & 31].push_back(static_cast<unsigned short>(i));
-        int fill[16];  // lanes used in round k
+        int T = 0;
+        for (int b = 0; b < 32; ++b) T = std::max(T, std::abs(static_cast<int>(bank_items[b].size()) - 16));
+        T = std::min(T, 16);
+        int mult[32][16];  // how many values of bank b go to round k
+        for (int b = 0; b < 32; ++b)
+            for (int k = 0; k < 16; ++k) mult[b][k] = 1;
+        int pe = 0, pa = 0;  // round-robin positions of the extras / of the absences inside the last T rounds
+        for (int b = 0; b < 32 && T > 0; ++b) {
+            const int c = static_cast<int>(bank_items[b].size());
+            for (int e = 0; e < c - 16; ++e) { ++mult[b][16 - T + pe % T]; ++pe; }
+            for (int a2 = 0; a2 < 16 - c; ++a2) { --mult[b][16 - T + pa % T]; ++pa; }
+        }
+        int fill[16];
         unsigned short round_items[16][32];
+        size_t next[32];
         for (int k = 0; k < 16; ++k) fill[k] = 0;
-        for (int b = 0; b < 32; ++b) {
-            for (size_t j = 0; j < bank_items[b].size(); ++j) {
-                if (j < 16) round_items[j][fill[j]++] = bank_items[b][j];
-                else overflow.push_back(bank_items[b][j]);
-            }
-        }
-        // overflow goes to the rounds with holes, spread so that one bank's extras land in different rounds
-        int k = 15;
-        for (unsigned short item : overflow) {
-            int tries = 0;
-            while (fill[k] >= 32 && tries < 16) { k = (k + 15) % 16; ++tries; }
-            round_items[k][fill[k]++] = item;
-            k = (k + 15) % 16;
-        }
+        for (int b = 0; b < 32; ++b) next[b] = 0;
+        for (int k = 0; k < 16; ++k)
+            for (int b = 0; b < 32; ++b)
+                for (int m = 0; m < mult[b][k]; ++m) round_items[k][fill[k]++] = bank_items[b][next[b]++];
         for (int r = 0; r < 16; ++r)
             for (int lane = 0; lane < 32; ++lane) {
                 const unsigned short i = round_items[r][lane];
