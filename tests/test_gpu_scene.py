@@ -290,3 +290,16 @@ def test_concurrent_analyses_like_the_reference(cuda):
         else:
             assert r["scene_cuts"] == want[i] or r["duplicates"]      # may match an earlier concurrent upload only by chance
             assert r["total_cuts"] == len(r["scene_cuts"])
+
+
+@pytest.mark.parametrize("H,W,P", [(270, 480, 480 * 3), (1080, 1920, 1920 * 3), (33, 101, 320)])
+def test_packed_rgb24_is_a_3w_byte_plane(cuda, H, W, P):
+    """Packed RGB24 / BGR24 sources (FFmpeg's select filter keeps them as ONE plane whose
+    visible width is av_image_get_linesize = 3*w bytes, count = 3*w*h): the same SAD and score kernels
+    with width = 3 * w -- no separate entry point is needed."""
+    g = torch.Generator().manual_seed(H + W)
+    frames = torch.empty((2, 6, H, P), dtype=torch.uint8)
+    frames[:, :3] = torch.randint(0, 256, (2, 1, H, P), dtype=torch.uint8, generator=g)   # three stills,
+    frames[:, 3:] = torch.randint(0, 256, (2, 1, H, P), dtype=torch.uint8, generator=g)   # a hard cut, three stills
+    o_sad, o_sel = _check(frames, cuda, width=3 * W)
+    assert o_sel[:, 3].all() and not o_sel[:, 4:].any()
