@@ -89,3 +89,33 @@ def test_fingerprint_layout_is_a_conflict_free_permutation():
             banks = ((fp[u * 512:(u + 1) * 512] >> 2) & 31).reshape(32, 16)  # [lane][round]
             worst.append(np.mean([np.bincount(banks[:, k], minlength=32).max() for k in range(16)]))
     assert worst and np.mean(worst) < 1.75, np.mean(worst)                  # ~1.58; random placement gives ~3.6
+
+
+def test_fingerprint_layout_edge_sizes():
+    """Units that are empty, partial, exactly full, or dominated by one bank (equal values, padding)
+    still come out as permutations that carry the right hashes."""
+    import numpy as np
+    from tvidz_b200 import _lib
+    rng = np.random.default_rng(11)
+    for n, kind in ((0, "rand"), (1, "rand"), (511, "rand"), (512, "rand"), (513, "rand"), (2048, "same"), (1500, "few")):
+        if kind == "same":
+            ts = np.full(n, 12.5)
+        elif kind == "few":
+            ts = rng.choice(np.array([1.0, 2.5, 1e9, 0.0]), n)
+        else:
+            ts = np.round(rng.uniform(0, 7200, n) * 30) / 30
+        ts = np.ascontiguousarray(ts, np.float64)
+        padded = max(1, -(-n // 512)) * 512
+        fp = np.full(padded, 0xffff, np.uint16)
+        perm = np.full(padded, 0xffff, np.uint16)
+        _lib.check(_lib.lib().tvz_debug_arrange_fingerprints(ts.ctypes.data if n else None, n, fp.ctypes.data,
+                                                             perm.ctypes.data))
+        bits = ts.view(np.uint64)
+        lo, hi = bits & np.uint64(0xffffffff), bits >> np.uint64(32)
+        h = (((lo * np.uint64(0x9E3779B1) + hi * np.uint64(0x85EBCA77)) & np.uint64(0xffffffff)) >> np.uint64(16)).astype(np.uint16)
+        for u in range(padded // 512):
+            p = perm[u * 512:(u + 1) * 512].astype(np.int64)
+            assert sorted(p.tolist()) == list(range(512)), (n, kind, u)
+            idx = u * 512 + p
+            want = np.where(idx < n, h[np.minimum(idx, max(n - 1, 0))] if n else 0, 0)
+            assert np.array_equal(fp[u * 512:(u + 1) * 512], want), (n, kind, u)
