@@ -135,3 +135,23 @@ def test_shim_end_to_end_on_the_gpu(cuda, tmp_path):
     assert ffmpeg_shim.run(argv, out=err, chunk_frames=48) == 0
     _, _, sel, _ = oracle.scene_batch(luma[None], None, 0.3)
     assert _reference_parse(err.getvalue()) == scene.cut_timestamps(sel[0])
+
+
+@pytest.mark.gpu
+def test_inspector_analyze_file_flags_the_reupload(cuda, tmp_path):
+    """analyze_file from a local file (app.py:197 onwards): first upload -> all cuts, no duplicates;
+    the same content uploaded again -> stops at its second cut and names the original (app.py:233-255)."""
+    from tvidz_b200.inspector import Inspector
+    luma = _synthetic_luma(n=200, h=180, w=320, seed=5)
+    path = str(tmp_path / 'clip.y4m')
+    _write_y4m(path, luma)
+    _, _, sel, _ = oracle.scene_batch(luma[None], None, 0.3)
+    cuts = scene.cut_timestamps(sel[0])
+    ins = Inspector()
+    first = ins.analyze_file('videos/1700000000-holiday.y4m', path)
+    assert first == {'status': 'done', 'scene_cuts': cuts, 'progress': 1.0, 'total_cuts': len(cuts), 'duplicates': [],
+                     'original_filename': '1700000000-holiday.y4m', 'clean_filename': 'holiday.y4m'}
+    again = ins.analyze_file('videos/1700000001-copy.y4m', path)
+    assert again['status'] == 'done' and again['scene_cuts'] == cuts[:2] and again['duplicates'] == ['holiday.y4m']
+    bad = ins.analyze_file('videos/x.mp4', str(tmp_path / 'missing.mp4'))
+    assert bad['status'] == 'error' and bad['total_cuts'] == 0

@@ -200,6 +200,54 @@ class Inspector:
                     'original_filename': filename, 'clean_filename': original}
 
 
+    def analyze_file(self, key: str, local_path: str, threshold: float = 0.3, fmt: str = "g6",
+                     chunk_frames: int = 64) -> dict:
+        """analyze_file (app.py:117-322) from the point where the upload sits in a local file
+        (app.py:197): host decode of the luma planes (ffmpeg_shim.open_frames: YUV4MPEG2 or OpenCV's
+        libavcodec), GPU scoring chunk by chunk, the cut timestamps FFmpeg's showinfo would print, the
+        per-cut duplicate loop -- and the result record of app.py:293-302."""
+        from . import ffmpeg_shim
+        filename = key.split('/')[-1] if key and '/' in key else key or 'unknown_file'   # app.py:122
+        original = filename
+        if '-' in filename and filename.split('-')[0].isdigit():                          # app.py:128-130
+            original = '-'.join(filename.split('-')[1:])
+        video = self.add_video(original)                                                  # app.py:150
+        try:
+            w, h, fps, frames = ffmpeg_shim.open_frames(local_path)
+            feed = ffmpeg_shim.gpu_chunk_scorer(threshold)
+            time_base = (fps.denominator, fps.numerator)
+            tokens, t0, k = [], 0, 0
+            import numpy as np
+            buf = np.empty((chunk_frames, h, w), np.uint8)
+
+            def flush(n):
+                nonlocal t0
+                for j in np.nonzero(np.asarray(feed(buf[:n])))[0]:
+                    tokens.append(scene.pts_time_string(t0 + int(j), time_base, fmt))   # the pts_time: token
+                t0 += n
+
+            for frame in frames:
+                buf[k] = frame
+                k += 1
+                if k == chunk_frames:
+                    flush(k)
+                    k = 0
+            if k:
+                flush(k)
+            final, dup_ids = self.analyze_cuts(video.id, tokens, min_match=2)             # app.py:228-255
+            names = []
+            for d in dup_ids:                                                             # app.py:241-245
+                dv = self.get_video_by_id(d)
+                if dv:
+                    names.append(dv.filename)
+            return {'status': 'done', 'scene_cuts': final, 'progress': 1.0, 'total_cuts': len(final),
+                    'duplicates': list(set(names)) if names else [], 'original_filename': filename,
+                    'clean_filename': original}
+        except Exception as e:                                                            # app.py:303-315
+            return {'status': 'error', 'error': str(e), 'progress': 0.0, 'total_cuts': 0, 'duplicates': [],
+                    'original_filename': filename, 'clean_filename': original}
+
+
 _default = Inspector()
 
 
@@ -233,3 +281,7 @@ def clear_db():
 
 def analyze_frames(key, frames, **kw):
     return _default.analyze_frames(key, frames, **kw)
+
+
+def analyze_file(key, local_path, **kw):
+    return _default.analyze_file(key, local_path, **kw)
