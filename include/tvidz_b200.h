@@ -101,15 +101,31 @@ typedef struct tvz_match_ws tvz_match_ws;   /* per-thread query workspace */
  * videos.id) onto the current device.  Stored values are canonicalised so that
  * bitwise equality equals Python float `==` (db.py:88): -0.0 -> +0.0, NaNs
  * dropped, repeats inside a row dropped (they never change a match count).
- * Device memory: 26 bytes per stored value (the value in row order, a 16-bit
- * fingerprint of it -- what a query streams -- and a 16-byte verification
- * record) + 12 bytes per row. */
+ * Device memory: 26 bytes per stored value (a 16-bit fingerprint -- what a query
+ * streams --, a 16-byte verification record {value, row}, and the value in row
+ * order for the early-exit kernel) + 13 bytes per row. */
 int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_video_id,
                        int64_t n_rows, tvz_catalog **out);
+/* The same with a mutable TAIL of `tail_values` stored values (and up to 4096 rows) behind the
+ * packed rows, for tvz_catalog_upsert. */
+int tvz_catalog_create_mutable(const double *h_ts, const int64_t *h_off, const int32_t *h_video_id,
+                               int64_t n_rows, int64_t tail_values, tvz_catalog **out);
 void tvz_catalog_destroy(tvz_catalog *cat);
-int64_t tvz_catalog_rows(const tvz_catalog *cat);
+int64_t tvz_catalog_rows(const tvz_catalog *cat);       /* packed rows + rows in the tail (replaced ones included) */
 int64_t tvz_catalog_values(const tvz_catalog *cat);     /* stored doubles after canonicalisation */
 int64_t tvz_catalog_algo_bytes(const tvz_catalog *cat); /* 8*values + 8*(rows+1), SURVEY.md 8d */
+int tvz_catalog_tiles(const tvz_catalog *cat);          /* CTAs one query launches */
+
+/* add_timestamps (db.py:43-64) on the device: the first live row of `video_id` is replaced
+ * (its verification records are overwritten in place so that it can never match again), or a new
+ * row is appended; the new row goes to the tail and is last in result order.  One small kernel
+ * whose values ride in its parameters; queries enqueued after the call returns see it.
+ * Contract: no query on this catalogue is in flight while an upsert runs (the Python Inspector
+ * serialises them).  TVZ_ERR_OVERFLOW: the tail is full even after dropping replaced rows --
+ * repack (create a new catalogue from the live rows). */
+int tvz_catalog_upsert(tvz_catalog *cat, int32_t video_id, const double *h_ts, int n);
+/* out4 = { rows in the tail, values in the tail, value capacity of the tail, replaced packed rows } */
+int tvz_catalog_tail_info(const tvz_catalog *cat, int64_t *out4);
 
 int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_ws **out);
 void tvz_match_ws_destroy(tvz_match_ws *ws);
@@ -125,23 +141,25 @@ int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q,
                       int64_t cap, int64_t *n_out);
 
 /* Batched find_duplicates: the reference runs one analysis thread per upload (app.py:43,472), so
- * concurrent queries are the normal case; up to 8 of them are answered by ONE pass over the
- * catalogue (one bit per query in the filter map), more are processed group by group.
+ * concurrent queries are the normal case; up to tvz_catalog_batch_size() (8) of them are answered by
+ * ONE pass over the fingerprints (one bit per query in the filter map, 16-bit counts), more are
+ * processed group by group.
  *   q_all / q_off : CSR of the queries (q_off has n_queries + 1 entries)
  *   out_off       : int64 [n_queries + 1]; hits of query i are out_*[out_off[i] .. out_off[i+1])
- * Each query may hold at most tvz_catalog_batch_limit() distinct values.  On TVZ_ERR_OVERFLOW
- * *need_per_query (if > the workspace's hit_capacity) and *need_total say how much room a retry
- * needs. */
+ * Each query may hold at most tvz_catalog_batch_limit() distinct values and 65535 values in all.
+ * On TVZ_ERR_OVERFLOW *need_per_query (if > the workspace's hit_capacity) and *need_total say how
+ * much room a retry needs. */
 int tvz_catalog_batch_limit(void);
+int tvz_catalog_batch_size(void);
 int tvz_catalog_match_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all, const int64_t *q_off,
                             int n_queries, int min_match, int32_t *out_video_id, int32_t *out_count,
                             int64_t *out_off, int64_t cap_total, int64_t *need_per_query, int64_t *need_total);
 
-/* Device-resident variant for pipelines, CUDA graphs and the sharded matcher:
- * enqueues the query -- normally ONE cooperative kernel launch that counts and
- * compacts (the keys of a query with <= 224 distinct values travel in the kernel
- * parameters) -- on `stream` and returns without synchronising.  Back-to-back
- * calls on one stream pipeline without a host-side wait.  The result is written to
+/* Device-resident variant for pipelines and the sharded matcher: enqueues the
+ * query -- ONE ordinary kernel launch that streams, counts and compacts (the keys
+ * of a query with <= 224 distinct values travel in the kernel parameters) -- on
+ * `stream` and returns without synchronising.  Back-to-back calls on one stream
+ * pipeline without a host-side wait.  The result is written to
  *   d_out : int32 [out_cap + 1][2] on the device (NULL = the workspace's own
  *           buffer, see tvz_match_ws_hits, capacity = hit_capacity):
  *             d_out[0]     = { n_hits saturated to INT32_MAX, 1 if n_hits > out_cap }
@@ -153,11 +171,15 @@ int tvz_catalog_match_batch(const tvz_catalog *cat, tvz_match_ws *ws, const doub
  */
 int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn,
                             int min_match, int32_t *d_out, int64_t out_cap, void *stream);
+/* ... and up to 8 queries at once: d_out is int32 [n_queries][out_cap + 1][2]. */
+int tvz_catalog_match_batch_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
+                                  const int64_t *q_off, int n_queries, int min_match, int32_t *d_out,
+                                  int64_t out_cap, void *stream);
 /* Sharded matcher with the gather fused into the kernel (one process per GPU, peers reachable
- * over NVLink): like tvz_catalog_match_async into the workspace's own record, but the
- * compaction phase also STORES this rank's record ({n_hits, overflow} + hits) into
- * every peer's gather buffer and its last block raises a per-rank flag there with a system-scope release;
- * a one-warp kernel enqueued behind it waits until the flags of all peers show `epoch`.
+ * over NVLink): like tvz_catalog_match_async into the workspace's own record, but every CTA also
+ * STORES its hits into every peer's gather buffer, the CTA that finishes last stores the header
+ * {n_hits, overflow} and raises a per-rank flag there with a system-scope release, and then
+ * waits (bounded) until the flags of all peers show `epoch` -- no second kernel, no collective.
  *   peer_record[p] : device address (peer memory) of THIS rank's slot, int32 [out_cap + 1][2],
  *                    inside peer p's gather buffer; peer_flag[p]: this rank's uint32 flag on peer p
  *   d_my_flags     : this rank's own flag array, uint32 [n_peers] (written by the peers)
@@ -167,9 +189,20 @@ int tvz_catalog_match_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, con
                                    int min_match, int n_peers, const uint64_t *peer_record,
                                    const uint64_t *peer_flag, const uint32_t *d_my_flags, int64_t out_cap,
                                    uint32_t epoch, void *stream);
+/* The batched form: this rank's slot on every peer is int32 [8][out_cap + 1][2]. */
+int tvz_catalog_match_batch_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
+                                         const int64_t *q_off, int n_queries, int min_match, int n_peers,
+                                         const uint64_t *peer_record, const uint64_t *peer_flag,
+                                         const uint32_t *d_my_flags, int64_t out_cap, uint32_t epoch,
+                                         void *stream);
+/* Strided device -> host copy of a slice of n fixed-size records: bytes [offset, offset + width) of
+ * every record, pitch_bytes apart on the device and in h_rec alike; sync != 0 waits for the stream.
+ * How the sharded matchers read every shard's header plus an optimistic first slice of every hit
+ * list with a single device-to-host transfer. */
+int tvz_copy_records_to_host(const void *d_rec, void *h_rec, int n_records, int64_t pitch_bytes,
+                             int64_t offset_bytes, int64_t width_bytes, int sync, void *stream);
 const int32_t *tvz_match_ws_hits(const tvz_match_ws *ws);
 const int64_t *tvz_match_ws_nhits(const tvz_match_ws *ws);
-const int32_t *tvz_match_ws_counts(const tvz_match_ws *ws);  /* int32 [rows] scratch (zero between calls) */
 
 /* ------------------------------------------------------------------ fragment mode
  * Offset-invariant matching of a clip's cut list against longer stored videos
@@ -204,6 +237,14 @@ int tvz_fragcat_match(tvz_fragcat *cat, const double *q, int qn, int min_match, 
 int tvz_fragcat_match_async(tvz_fragcat *cat, const double *h_q, int qn, int min_match, int tol_ticks,
                             int tol_gap_ticks, int anchor_intervals, int zero_offset_only, int32_t *d_out,
                             int64_t out_cap, void *stream);
+
+/* Sharded fragment matcher with the gather fused into the compaction kernel (see
+ * tvz_catalog_match_gather_async): this rank's slot on every peer is int32 [3 * (out_cap + 1)] in the
+ * layout above; a one-warp kernel behind the compaction waits for the peers' flags. */
+int tvz_fragcat_match_gather_async(tvz_fragcat *cat, const double *h_q, int qn, int min_match, int tol_ticks,
+                                   int tol_gap_ticks, int anchor_intervals, int zero_offset_only, int n_peers,
+                                   const uint64_t *peer_record, const uint64_t *peer_flag,
+                                   const uint32_t *d_my_flags, int64_t out_cap, uint32_t epoch, void *stream);
 
 #ifdef __cplusplus
 }

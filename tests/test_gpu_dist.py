@@ -21,6 +21,7 @@ def _free_port():
 
 
 def _worker(rank, world, port, q_out):
+    import numpy as np
     import torch.distributed as dist
 
     import oracle
@@ -45,12 +46,22 @@ def _worker(rank, world, port, q_out):
             torch.cuda.synchronize()
             want = oracle.find_duplicates_csr(ts, off, vid, ts[off[9]:off[10]], 2)
             ok.append((gather, "pipelined", int(g[:, 0, 0].sum().item()) == len(want)))
+            # 8 queries per pass over every shard (and a second, ragged group), full lists against the oracle
+            picks = [3, 17, 4000, 29_999, 30_000, 45_678, 59_999, 12, 31, 50_000, 7]
+            qs = [ts[off[r]:off[r + 1]] for r in picks] + [np.zeros(0)]
+            many = sc.find_duplicates_many(qs, 2)
+            ok.append((gather, "match_many", many == [oracle.find_duplicates_csr(ts, off, vid, q, 2) for q in qs]))
         fts, foff, fvid = synth.synth_catalogue(3000, len_range=(600, 1400), gap_range=(15, 150), seed=34)
         fq = clip_query(fts[foff[1234]:foff[1235]], 20_000)
-        fc = ShardedFragmentCatalogue(fts, foff, fvid, hit_capacity=8, device=rank)
-        got = fc.find_fragments(fq, 4)
         want = oracle.find_fragments_csr(fts, foff, fvid, fq, min_match=4)
-        ok.append(("fragment", [(v, s, round(o * 1000)) for v, s, o in got] == want and len(want) >= 1))
+        for gather in ("nccl", "fused"):
+            fc = ShardedFragmentCatalogue(fts, foff, fvid, hit_capacity=8, device=rank, gather=gather)
+            for _ in range(3):                                    # consecutive epochs alternate buffer sets
+                got = fc.find_fragments(fq, 4)
+                ok.append(("fragment-" + gather, [(v, s, round(o * 1000)) for v, s, o in got] == want and len(want) >= 1))
+            ok.append(("fragment-" + gather + "-anchor1",
+                       [(v, s, round(o * 1000)) for v, s, o in fc.find_fragments(fq, 4, anchor=1)]
+                       == oracle.find_fragments_csr(fts, foff, fvid, fq, min_match=4, anchor=1)))
         q_out.put((rank, ok))
     except Exception as e:
         q_out.put((rank, [("exception", repr(e), False)]))
@@ -60,7 +71,7 @@ def _worker(rank, world, port, q_out):
 
 
 def test_sharded_matcher_nccl_and_fused(cuda):
-    world = min(torch.cuda.device_count(), 2)
+    world = min(torch.cuda.device_count(), 8)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

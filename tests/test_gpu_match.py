@@ -179,18 +179,18 @@ def test_full_size_million_rows(cuda):
     cat.close()
 
 
-def test_reference_style_per_cut_loop_uses_the_overlay(cuda, stream_golden):
+def test_reference_style_per_cut_loop_is_a_device_upsert(cuda, stream_golden):
     """The unmodified shape of app.py:228-255 -- add_timestamps() then find_duplicates() after every
-    new cut -- against a 30k-row catalogue: same verdicts as the oracle's streaming loop, and the big
-    catalogue is packed exactly once (row rewrites go to the overlay + tombstones)."""
+    new cut -- against a 30k-row catalogue: same verdicts as the oracle's streaming loop, and the
+    catalogue is packed exactly once (row rewrites are device-side upserts into the tail)."""
     ts, off, vid = synth.synth_catalogue(30_000, seed=12)
     ins = Inspector()
     rows = []
     for r in range(30_000):
         row = ts[off[r]:off[r + 1]].tolist()
-        ins._rows[r + 1] = row
         rows.append((r + 1, row))
-    ins._next_id = 30_001
+    ins.load_rows(rows)
+    assert ins._next_id == 30_001
     assert ins.find_duplicates([1.0], 1) is not None and ins.repacks == 1
     for src in (10, 20_000, 29_999):
         me = ins.add_video("upload-%d.mp4" % src)
@@ -213,12 +213,148 @@ def test_reference_style_per_cut_loop_uses_the_overlay(cuda, stream_golden):
                                                    match_oracle.find_duplicates(rows, rows[10][1], 5) if d[0] != 11]
     assert (11, 2) in ins.find_duplicates([123456.5, 123457.5], 2)
     assert ins.repacks == 1
-    small = Inspector(overlay_limit=2)                      # the overlay folds into a fresh pack when it outgrows its limit
-    for i in range(6):
+    info = ins._cat.tail_info()
+    assert info["rows"] == 4 and info["replaced_packed_rows"] == 1      # 3 uploads (each rewritten in place) + row 11
+    small = Inspector(tail_values=512, hit_capacity=64)     # a tail of one unit: fills, is compacted, finally repacks
+    for i in range(300):
         v = small.add_video("v%d" % i)
         small.add_timestamps(v.id, [float(i), float(i) + 0.5])
         assert small.find_duplicates([float(i), float(i) + 0.5], 2) == [(v.id, 2)]
-    assert small.repacks == 2 and small.find_duplicates([0.0, 0.5, 3.0, 3.5], 2) == [(1, 2), (4, 2)]
+    assert small.repacks == 2 and small.find_duplicates([0.0, 0.5, 3.0, 3.5, 299.0, 299.5], 2) == [(1, 2), (4, 2), (300, 2)]
+
+
+def _model_find(rows, q, mm, python=False):
+    """rows: dict video_id -> list, in order of last write (what the Inspector promises)."""
+    if python:
+        return match_oracle.find_duplicates(match_oracle.hydrate(list(rows.items())), q, mm)
+    return oracle.find_duplicates_csr(*rows_to_csr(list(rows.items())), q, mm)
+
+
+@pytest.mark.parametrize("tail_values,seed", [(1 << 16, 1), (2048, 2)])
+def test_device_upserts_against_a_host_model(cuda, tail_values, seed):
+    """Random add_timestamps traffic (db.py:43-64: replace-or-append) straight on the mutable device
+    catalogue -- packed rows replaced, tail rows replaced, the last row rewritten in place, rows longer
+    than the kernel-parameter path, empty rows -- against a dict that replays the same writes.  The small
+    tail forces tail compactions on the way."""
+    rng = np.random.default_rng(seed)
+    ts, off, vid = synth.synth_catalogue(5000, seed=40 + seed, len_range=(0, 40))
+    model = {int(vid[r]): ts[off[r]:off[r + 1]].tolist() for r in range(5000)}
+    cat = Catalogue(ts, off, vid, mutable=True, tail_values=tail_values, hit_capacity=8192)
+    pool = np.unique(ts)
+    last, repacks = None, 0
+    for step in range(400):
+        kind = rng.integers(0, 5)
+        if kind == 0 or last is None:
+            v = int(rng.integers(1, 5001))                               # a packed (or already moved) row
+        elif kind == 1:
+            v = last                                                     # the row written last: in place
+        elif kind == 2:
+            v = 6000 + int(rng.integers(0, 50))                          # new videos / earlier tail rows
+        else:
+            v = int(rng.choice(list(model.keys())))
+        n = int(rng.choice([0, 1, 3, 17, 60, 300]))
+        row = np.sort(rng.choice(pool, n, replace=False)).tolist() if n else []
+        if n and rng.integers(0, 4) == 0:
+            row = row + row[:2] + [float("nan"), -0.0]                   # repeats and specials are canonicalised
+        ok = cat.upsert(v, row)
+        model.pop(v, None)
+        model[v] = row
+        last = v
+        if not ok:                                                       # tail full of live rows: repack, as the Inspector does
+            cat.close()
+            cat = Catalogue.from_rows(list(model.items()), mutable=True, tail_values=tail_values, hit_capacity=8192)
+            repacks += 1
+        if step % 7 == 0 or step > 390:
+            probe = model[last] if model[last] else model[int(rng.choice(list(model.keys())))]
+            for mm in (2, 1, 0):
+                assert cat.find_duplicates(probe, mm) == _model_find(model, probe, mm), (step, mm)
+    v, c, k = cat.match(model[last] or [1.0], 1, with_kth=True)          # the early-exit kernel reads tail rows too
+    items = list(model.items())
+    mts, moff, mvid = rows_to_csr(items)
+    counts = oracle.match_counts(mts, moff, model[last] or [1.0])
+    keep = np.nonzero(counts >= 1)[0]
+    assert np.array_equal(v, mvid[keep]) and np.array_equal(k, oracle.match_kth(mts, moff, model[last] or [1.0], 1)[keep])
+    got = cat.find_duplicates_many([model[last], items[3][1], []], 1)    # the batched kernel sees the same catalogue
+    assert got == [_model_find(model, q, 1) for q in (model[last], items[3][1], [])]
+    assert cat.find_duplicates(items[3][1], 1) == _model_find(model, items[3][1], 1, python=True)
+    info = cat.tail_info()
+    assert info["values"] <= info["capacity"] and (repacks > 0) == (tail_values == 2048)
+    cat.close()
+
+
+def test_upsert_overflow_reports_and_immutable_refuses(cuda):
+    cat = Catalogue.from_rows([(1, [1.0, 2.0])], mutable=True, tail_values=512)
+    for i in range(8):                                                   # 8 live rows x 64 values fill the 512-value tail
+        assert cat.upsert(100 + i, [float(1000 * i + k) for k in range(64)])
+    assert cat.upsert(200, [5.0]) is False                               # nothing to drop: the caller must repack
+    assert cat.upsert(100, [7.0, 8.0]) is True                           # replacing a live row frees room (tail compaction)
+    assert cat.find_duplicates([7.0, 8.0, 1.0, 2.0], 2) == [(1, 2), (100, 2)]
+    cat.close()
+    frozen = Catalogue.from_rows([(1, [1.0])])
+    with pytest.raises(Exception):
+        frozen.upsert(1, [2.0])
+    frozen.close()
+
+
+@pytest.mark.parametrize("shape", ["empty_rows", "giant_row", "short_rows", "two_values"])
+def test_tile_boundaries(cuda, shape):
+    """Catalogues whose rows fall awkwardly on the tile grid: thousands of empty rows, one row far larger
+    than a tile's share, more rows than 4096 per tile would allow, and the smallest catalogue."""
+    rng = np.random.default_rng(5)
+    if shape == "empty_rows":
+        lens = np.zeros(30_000, np.int64)
+        lens[rng.integers(0, 30_000, 500)] = rng.integers(1, 90, 500)
+    elif shape == "giant_row":
+        lens = rng.integers(1, 30, 3000)
+        lens[1500] = 400_000
+    elif shape == "short_rows":
+        lens = rng.integers(0, 3, 700_000)
+    else:
+        lens = np.array([1, 1], np.int64)
+    off = np.zeros(lens.shape[0] + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    ts = np.round(rng.integers(0, 3_000_000, int(off[-1])) / 30.0, 4)
+    vid = np.arange(1, lens.shape[0] + 1, dtype=np.int32)
+    cat = Catalogue(ts, off, vid, hit_capacity=1 << 12)
+    r = int(np.argmax(lens))
+    queries = [ts[off[r]:off[r + 1]][:200], ts[rng.integers(0, ts.shape[0], 50)], ts[:1]]
+    for q in queries:
+        for mm in (1, 2, 0):
+            assert cat.find_duplicates(q, mm) == oracle.find_duplicates_csr(ts, off, vid, q, mm), (shape, mm)
+    got = cat.find_duplicates_many(queries, 1)
+    assert got == [oracle.find_duplicates_csr(ts, off, vid, q, 1) for q in queries]
+    cat.close()
+
+
+def test_concurrent_callers_are_combined_into_batched_passes(cuda):
+    """8 analysis threads (app.py:43,472) calling find_duplicates at once on one Inspector: every caller
+    gets exactly its own answer, and the device answered several of them per catalogue pass."""
+    ts, off, vid = synth.synth_catalogue(200_000, seed=17)
+    ins = Inspector()
+    ins.load_rows([(int(vid[r]), ts[off[r]:off[r + 1]].tolist()) for r in range(200_000)])
+    ins.find_duplicates([1.0], 1)                                        # pack once, outside the race
+    picks = [3, 1999, 50_000, 77_777, 120_000, 150_001, 180_000, 199_999]
+    want = {r: oracle.find_duplicates_csr(ts, off, vid, ts[off[r]:off[r + 1]], 2) for r in picks}
+    got, errs = {}, []
+    start = threading.Barrier(len(picks))
+
+    def work(r):
+        try:
+            start.wait()
+            for i in range(20):
+                res = ins.find_duplicates(ts[off[r]:off[r + 1]].tolist(), 2)
+                if i == 7 and r == picks[0]:                             # an upsert in the middle of the traffic
+                    ins.add_timestamps(999_999, [0.25, 0.75])
+                got[r] = res
+        except Exception as e:                                           # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(r,)) for r in picks]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs and got == want
+    assert sum(ins.batches) == 1 + 20 * len(picks) and max(ins.batches) > 1 and ins.repacks == 1
+    assert ins.find_duplicates([0.25, 0.75], 2) == [(999_999, 2)]
 
 
 def test_batched_queries_equal_single_queries(cuda, match_golden):
@@ -237,6 +373,12 @@ def test_batched_queries_equal_single_queries(cuda, match_golden):
             assert g == oracle.find_duplicates_csr(ts, off, vid, q, mm)
     assert cat.find_duplicates_many([], 2) == []
     cat.close()
+    for n_rows in (150, 20_001):                                 # row counts that are no multiple of 4 (or 16)
+        t2, o2, v2 = synth.synth_catalogue(n_rows, seed=n_rows)
+        cat = Catalogue(t2, o2, v2, hit_capacity=64)
+        qs = [t2[o2[r]:o2[r + 1]].copy() for r in (0, n_rows // 2, n_rows - 1)]
+        assert cat.find_duplicates_many(qs, 2) == [oracle.find_duplicates_csr(t2, o2, v2, q, 2) for q in qs]
+        cat.close()
     for c in match_golden[:12]:                                  # the reference's own vectors, batched together
         rows = _rows(c)
         cat = Catalogue.from_rows(rows)

@@ -20,33 +20,44 @@ SYMBOLS = [
     ("tvz_scene_select", _i, [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp]),
     ("tvz_scene_score_host", _i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i, _d, _i, _vp, _vp, _vp]),
     ("tvz_catalog_create", _i, [_vp, _vp, _vp, _i64, C.POINTER(_vp)]),
+    ("tvz_catalog_create_mutable", _i, [_vp, _vp, _vp, _i64, _i64, C.POINTER(_vp)]),
     ("tvz_catalog_destroy", None, [_vp]),
     ("tvz_catalog_rows", _i64, [_vp]),
     ("tvz_catalog_values", _i64, [_vp]),
     ("tvz_catalog_algo_bytes", _i64, [_vp]),
+    ("tvz_catalog_tiles", _i, [_vp]),
+    ("tvz_catalog_upsert", _i, [_vp, C.c_int32, _vp, _i]),
+    ("tvz_catalog_tail_info", _i, [_vp, _vp]),
     ("tvz_match_ws_create", _i, [_vp, _i64, C.POINTER(_vp)]),
     ("tvz_match_ws_destroy", None, [_vp]),
     ("tvz_catalog_match", _i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     ("tvz_catalog_batch_limit", _i, []),
+    ("tvz_catalog_batch_size", _i, []),
     ("tvz_catalog_match_batch", _i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i64, C.POINTER(_i64),
                                      C.POINTER(_i64)]),
     ("tvz_catalog_match_async", _i, [_vp, _vp, _vp, _i, _i, _vp, _i64, _vp]),
+    ("tvz_catalog_match_batch_async", _i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i64, _vp]),
     ("tvz_catalog_match_gather_async", _i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64, C.c_uint32, _vp]),
+    ("tvz_catalog_match_batch_gather_async", _i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64, C.c_uint32,
+                                                  _vp]),
+    ("tvz_copy_records_to_host", _i, [_vp, _vp, _i, _i64, _i64, _i64, _i, _vp]),
     ("tvz_match_ws_hits", _vp, [_vp]),
     ("tvz_match_ws_nhits", _vp, [_vp]),
-    ("tvz_match_ws_counts", _vp, [_vp]),
     ("tvz_fragcat_create", _i, [_vp, _vp, _vp, _i64, _d, _i64, C.POINTER(_vp)]),
     ("tvz_fragcat_destroy", None, [_vp]),
     ("tvz_fragcat_rows", _i64, [_vp]),
     ("tvz_fragcat_values", _i64, [_vp]),
     ("tvz_fragcat_match", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     ("tvz_fragcat_match_async", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
+    ("tvz_fragcat_match_gather_async", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, C.c_uint32, _vp]),
 ]
 # debug hooks outside the public header
 _DEBUG_SYMBOLS = [("tvz_debug_sad_tuning", _i, [_i, _i, _i, _i]),
                   ("tvz_debug_match_timing", _i, [_vp, _i]),
                   ("tvz_debug_match_count_ms", _i, [_vp, C.POINTER(C.c_float)]),
-                  ("tvz_debug_arrange_fingerprints", _i, [_vp, _i64, _vp, _vp])]
+                  ("tvz_debug_tile_trace", _i, [_vp, _vp]),
+                  ("tvz_debug_arrange_fingerprints", _i, [_vp, _i64, _vp, _vp]),
+                  ("tvz_debug_build_tiles", _i, [_vp, _i64, _i, _vp, _i])]
 
 TVZ_ERR_OVERFLOW = -4
 _lib = None

@@ -576,7 +576,7 @@ int frag_reserve(tvz_fragcat *c, long long cap) {
 }
 
 int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int tol, int tol_gap, int anchor,
-                 int zero_only, int *d_out, long long out_cap, cudaStream_t st) {
+                 int zero_only, int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr) {
     TVZ_REQUIRE(qn >= 0 && (qn == 0 || h_q), "bad query");
     TVZ_REQUIRE(tol >= 0 && tol_gap >= 0, "negative tolerance");
     TVZ_REQUIRE(anchor >= 1 && anchor <= kMaxAnchor, "anchor_intervals must be 1..%d", kMaxAnchor);
@@ -597,6 +597,7 @@ int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int t
     fq.zero_only = zero_only;
     std::copy(q.begin(), q.end(), fq.q);
     if (c->n_rows == 0) {
+        TVZ_REQUIRE(!gather, "an empty shard cannot take part in the fused gather");
         TVZ_CUDA(cudaMemsetAsync(d_out, 0, 8, st));
         TVZ_CUDA(cudaMemsetAsync(c->d_nhits, 0, 8, st));
         return TVZ_OK;
@@ -618,11 +619,11 @@ int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int t
             }();
             const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, static_cast<long long>(kStreamMinBlocks) * num_sms())));
             auto kern = anchor == 2 ? fragment_stream_kernel<2> : fragment_stream_kernel<3>;
-            TVZ_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), 0, st, false, c->d_ticks, c->n_vals, c->n_padded, c->d_off,
+            TVZ_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), 0, st, c->d_ticks, c->n_vals, c->n_padded, c->d_off,
                                 c->d_block_row, c->n_rows, fq, shift, c->d_keys, l2_ahead, queue_cap));
         }
         return compact_enqueue_keys(c->d_keys, c->n_rows, min_match, c->d_vid, d_out, c->d_rows, out_cap, c->d_nhits,
-                                    c->d_state, c->d_ticket, d_out + 2 * (out_cap + 1), st);
+                                    c->d_state, c->d_ticket, d_out + 2 * (out_cap + 1), st, gather);
     }
     const long long want = (c->n_rows + kFragWarps - 1) / kFragWarps;
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, 4ll * num_sms())));
@@ -631,7 +632,7 @@ int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int t
     TVZ_CUDA(cudaGetLastError());
     // records at d_out[0 .. 2*(out_cap+1)), deltas behind them at d_out + 2*(out_cap+1)
     return compact_enqueue(c->d_score, c->n_rows, min_match, c->d_vid, d_out, c->d_rows, out_cap, c->d_nhits,
-                           c->d_state, c->d_ticket, c->d_delta, d_out + 2 * (out_cap + 1), st);
+                           c->d_state, c->d_ticket, c->d_delta, d_out + 2 * (out_cap + 1), st, gather);
 }
 
 }  // namespace
@@ -750,6 +751,33 @@ int tvz_fragcat_match_async(tvz_fragcat *c, const double *h_q, int qn, int min_m
     if (rc) return rc;
     return frag_enqueue(c, h_q, qn, min_match, tol_ticks, tol_gap_ticks, anchor_intervals, zero_offset_only, d_out,
                         out_cap, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int tvz_fragcat_match_gather_async(tvz_fragcat *c, const double *h_q, int qn, int min_match, int tol_ticks,
+                                   int tol_gap_ticks, int anchor_intervals, int zero_offset_only, int n_peers,
+                                   const uint64_t *peer_record, const uint64_t *peer_flag, const uint32_t *d_my_flags,
+                                   int64_t out_cap, uint32_t epoch, void *stream) {
+    return guarded([&]() -> int {
+    TVZ_REQUIRE(c && out_cap >= 1, "bad arguments");
+    TVZ_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers, "n_peers %d outside [1, %d]", n_peers, kMaxPeers);
+    TVZ_REQUIRE(peer_record && peer_flag && d_my_flags, "null pointer");
+    TVZ_REQUIRE(c->n_rows > 0, "the fused gather needs a non-empty shard");
+    GatherTargets gt;
+    gt.n_peers = n_peers;
+    gt.epoch = epoch;
+    for (int p = 0; p < n_peers; ++p) {
+        gt.record[p] = reinterpret_cast<int *>(static_cast<uintptr_t>(peer_record[p]));
+        gt.flag[p] = reinterpret_cast<unsigned *>(static_cast<uintptr_t>(peer_flag[p]));
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    int rc = frag_reserve(c, out_cap);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = frag_enqueue(c, h_q, qn, min_match, tol_ticks, tol_gap_ticks, anchor_intervals, zero_offset_only, c->d_out,
+                      out_cap, st, &gt);
+    if (rc) return rc;
+    return gather_wait_enqueue(d_my_flags, n_peers, epoch, st);
     });
 }
 

@@ -1,24 +1,44 @@
 // Stage 2: find_duplicates over a device-resident packed catalogue.
 //
 // Replaces inspector/db.py:76-94 (full-table fetch at db.py:83 + the O(N*q*L) Python
-// membership loop at db.py:85-91).  Semantics:
+// membership loop at db.py:85-91) and the row upsert of db.py:43-64.  Semantics:
 //     match_count(row) = #{ i : q[i] == some element of row }      (float ==)
 //     result = [(video_id, match_count) for rows with match_count >= min_match]
 //
 // Data layout in HBM (one shard per GPU):
-//     ts   : uint64 [n_vals]  IEEE-754 bit patterns of the stored timestamps, canonicalised
-//            at pack time (-0.0 -> +0.0, NaN dropped, in-row repeats dropped) so that bitwise
-//            equality == Python float equality and every stored value can add at most once
-//     fp   : uint16 [n_vals]  filter_hash(ts[i]): what the single-query count kernel streams
-//     off  : int64 [n_rows+1] CSR row offsets into ts
-//     vid  : int32 [n_rows]   videos.id of each row
-// Because in-row repeats are gone, match_count(row) = sum over stored values v of
-// mult(v), where mult(v) = number of query positions equal to v.  The count kernel is
-// therefore a pure streaming pass: 256-bit coalesced loads, a 64 KB shared-memory byte map of
-// the query rejects ~all values with one LDS.U8, and the rare survivors are looked up exactly
-// and added to counts[row] with a RED.  One query streams the 2-byte fingerprints (`fp`) and
-// touches `ts` only for survivors; the batched kernel (8 queries per pass) streams `ts` itself.
+//     fp   : uint16 [units * 512]  filter_hash of every stored value -- what a query streams (2 B per
+//            value); inside each 512-value unit the order is chosen for conflict-free lookups
+//     rec  : {u64 value, u32 row} [units * 512] in the same order -- what a surviving fingerprint is
+//            verified against (IEEE-754 bit patterns, canonicalised at pack time: -0.0 -> +0.0, NaN
+//            dropped, in-row repeats dropped, so bitwise equality == Python float equality and every
+//            stored value adds at most once)
+//     ts   : u64 [values] in row order + off i64 [rows + 1] (CSR): the per-cut early-exit kernel
+//     vid  : int32 [rows]; dead : u8 [rows] (rows replaced by an upsert)
+//     tiles: {row_lo, n_rows, unit_lo, unit_hi}: the catalogue cut into <= 4096-row pieces of equal
+//            stored-value count, one CTA each
+// Because in-row repeats are gone, match_count(row) = sum over stored values v of mult(v), where
+// mult(v) = number of query positions equal to v.
+//
+// ONE kernel per query (match_tile_kernel): a CTA owns WHOLE ROWS, so their counts live in its shared
+// memory -- no global counts[] array to zero, re-read and compact, no grid-wide barrier, no
+// cooperative launch.  It streams the fingerprints of its rows (256-bit loads, a 64 KB byte map of
+// the query rejects ~all values with one LDS.U8), verifies the rare survivors against `rec`, then
+// compacts its own rows: qualifying rows are counted, the tile's total is published, the totals of
+// all earlier tiles are read in ONE parallel step (every thread polls one predecessor: a single
+// global round trip instead of a look-back chain), and the hits go to their final position in
+// catalogue order.  With the fused multi-GPU gather the same kernel stores every hit into all peers'
+// buffers over NVLink and its last CTA publishes header + flag and waits for the peers' flags.
+// The kernel is templated on the number of queries answered per pass (1, or up to 8: one bit per
+// query in the byte map, 16-bit counts).
+//
+// The last tile is the mutable TAIL: rows written by tvz_catalog_upsert (one small kernel, keys in its
+// parameters) go there, the row they replace is neutralised in place (its verification records are
+// overwritten with a NaN pattern that equals no query value), so the reference's per-cut
+// add_timestamps() + find_duplicates() loop (app.py:234-235) never repacks the catalogue.
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -28,21 +48,15 @@ namespace tvz {
 namespace {
 
 constexpr int kMapEntries = 1 << 16;         // byte-map filter of the query: 64 KB of shared memory
-#ifndef TVZ_MAX_KEYS
-#define TVZ_MAX_KEYS 2048
-#endif
-constexpr int kMaxKeys = TVZ_MAX_KEYS;       // distinct query values per launch
-constexpr int kCountThreads = 512;            // batched kernel (streams the 8-byte values)
-constexpr int kCountUnroll = 8;               // 8 x 16 B (= 4 x 256-bit loads) in flight per thread
-constexpr int kChunkPairs = kCountThreads * kCountUnroll;  // 4096 pairs = 8192 values per CTA iteration
-constexpr int kCountWarps = kCountThreads / 32;
-constexpr int kWarpQueue = 64;               // filter survivors parked per warp
-constexpr int kBlockShift = 7;               // coarse row index: one entry per 128 stored values
-// 16384 rows per block: the look-back walks its predecessors 32 at a time, and every hop is a dependent
-// global round trip -- 1 M rows are 62 blocks (<= 2 hops) instead of 489 (<= 15 hops, ~8 us)
-constexpr int kScanThreads = 1024;
-constexpr int kScanRowsPerThread = 16;
-constexpr int kScanRowsPerBlock = kScanThreads * kScanRowsPerThread;
+constexpr int kFpPerUnit = 32 * 16;          // fingerprints per warp-wide 256-bit load
+constexpr int kTileRows = 4096;              // rows whose counts one CTA keeps in shared memory
+constexpr int kTileKeys = 1024;              // distinct values of ONE query kept in shared memory (more: searched in global memory)
+constexpr int kParamKeys = 224;              // distinct values that ride in the kernel parameters; per-query limit of a batch
+constexpr int kBatch = 8;                    // queries per batched pass
+constexpr int kMinTileUnits = 16;            // small catalogues: at least one unit per warp and tile
+constexpr int kMaxTailTiles = 16;            // the mutable tail: up to 16 tiles = 65536 rows between repacks
+constexpr int kTailRows = kMaxTailTiles * kTileRows;
+constexpr int kMaxGridParam = 320;           // tiles whose unit range rides in the kernel parameters (>= 2 CTAs x 148 SMs)
 constexpr unsigned long long kPadPattern = 0x7ff8dead0000beefull;  // a NaN: never equals a stored value
 
 // Two IMADs and a shift: good enough on frame-quantised timestamps and on x.0 / x.5 values
@@ -52,82 +66,15 @@ __host__ __device__ __forceinline__ uint32_t filter_hash(unsigned long long v) {
     return (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> 16;
 }
 
-// counts[row] += mult(v) for every stored value v that equals a query value.
-//
-// Streaming pass over `ts` (padded to whole chunks, so the hot loop has no bounds checks):
-// per value one hash, one LDS.U8 and a warp vote; the next chunk's 128-bit loads are already
-// in flight while the current one is probed.  Survivors (true matches plus ~0.1% false
-// positives) are parked in a per-warp shared-memory queue -- slots handed out from the vote
-// mask, no atomics -- and resolved 32 at a time by the whole warp: exact key lookup, then the
-// row through a coarse index (row of every 256th value) and a short search in `off`.  A hit
-// therefore never stalls the other 31 lanes, and no CTA-wide barrier sits in the loop.
 // Short queries (the common case: a video has tens of cuts) ride in the kernel parameters,
-// which saves the two host->device copies in front of the launch.
-constexpr int kParamKeys = 224;
+// which saves the host->device copy in front of the launch.
 struct SmallQuery {
     unsigned long long keys[kParamKeys];
     int mult[kParamKeys];
 };
 
-// 256-bit streaming load (sm_100 LDG.E.256): no L1 allocation -- this kernel leaves L1 almost
-// no room, shared memory takes ~213 of the SM's 228 KB -- and evict-first in L2.
-struct U64x4 {
-    unsigned long long a, b, c, d;
-};
-__device__ __forceinline__ U64x4 ld_stream_256(const void *p) {
-    U64x4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
-                 : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d)
-                 : "l"(p));
-    return r;
-}
-
-// Which 32-byte unit of the CTA's chunk thread t loads as its j-th (batched kernel).
-__device__ __forceinline__ int unit_index(int j) { return j * kCountThreads + threadIdx.x; }
-
-// ---- single query: streaming pass over the 16-bit FINGERPRINTS of the stored values ----
-//
-// The byte-map filter only ever looks at filter_hash(v), 16 bits of a value.  The catalogue
-// therefore also stores fp[i] = filter_hash(ts[i]) as a uint16 array (+2 B per stored value), and the
-// count kernel streams THAT: 2 bytes of HBM traffic per stored timestamp instead of 8 -- 128 MB
-// instead of 512 MB for the 1 M-row catalogue.  Nothing is lost: a fingerprint that passes the
-// filter (true matches + ~n_keys/65536 false positives, ~0.3 % of values) is verified against the
-// real 8-byte value, fetched from `ts` only then, with the exact key lookup as before.
-//
-// A warp-wide 256-bit load brings 512 fingerprints (16 per lane).  Units are dealt round-robin to
-// all warps of the grid (unit g = (it * kFpUnits + j) * n_warps + warp), so the grid sweeps one
-// contiguous window per load slot and every warp ends within one unit of every other.  Per
-// fingerprint: extract, LDS.U8, shift-or into the lane's 16-bit survivor mask; one vote per unit.
-// Survivors are parked inline (slots from a shuffle scan) as element indices in a per-warp queue and
-// resolved 32 at a time -- normally once, when the warp has finished streaming: load the value,
-// binary search of the sorted query keys, row through the coarse index + a short search in `off`,
-// RED.ADD counts[row] += mult.
-// launch shape (overridable for tuning sweeps: scripts/sweep_match.py builds variants)
-#ifndef TVZ_FP_THREADS
-#define TVZ_FP_THREADS 512
-#endif
-#ifndef TVZ_FP_UNITS
-#define TVZ_FP_UNITS 2   // measured: 2 -> 48.7 us, 4 -> 59.4 us (spills at 64 registers), 8 at 256 threads -> 53.2 us
-#endif
-constexpr int kFpThreads = TVZ_FP_THREADS;
-constexpr int kFpWarps = kFpThreads / 32;
-constexpr int kFpUnits = TVZ_FP_UNITS;       // 256-bit loads in flight per thread
-constexpr int kFpPerUnit = 32 * 16;          // fingerprints per warp-wide load
-#ifndef TVZ_FP_QUEUE
-#define TVZ_FP_QUEUE 128
-#endif
-#ifndef TVZ_FP_MINB
-#define TVZ_FP_MINB (TVZ_FP_THREADS >= 1024 ? 1 : 2)
-#endif
-constexpr int kFpQueue = TVZ_FP_QUEUE;       // survivors parked per warp
-
-struct alignas(16) FpSmem {
-    unsigned char map[kMapEntries];   // first: zeroed with 16-byte stores
-    unsigned long long keys[kMaxKeys];
-    long long qe[kFpWarps][kFpQueue];
-    int mult[kMaxKeys];
-};
-
+// 256-bit streaming load (sm_100 LDG.E.256): no L1 allocation -- shared memory takes ~205 of the SM's
+// 228 KB -- and evict-first in L2.
 struct U32x8 {
     unsigned w[8];
 };
@@ -150,258 +97,71 @@ struct alignas(16) VerifyRec {
     unsigned long long ts;
     unsigned row, pad;
 };
-struct FpCtx {
+
+// One CTA's share of the catalogue: whole rows [row_lo, row_lo + n_rows) and the fingerprint units that
+// hold their values.  Neighbouring tiles may share a boundary unit; each counts only its own rows.
+struct alignas(16) TileDesc {
+    int row_lo, n_rows;
+    unsigned unit_lo, unit_hi;
+};
+struct TileUnits {                // unit range of tile t < kMaxGridParam, in the kernel parameters: the
+    unsigned lo[kMaxGridParam];   // first loads are issued before anything else is read
+    unsigned hi[kMaxGridParam];
+};
+
+template <int kQ>
+struct TileShape {
+    static constexpr int kThreads = kQ == 1 ? 512 : 1024;
+    static constexpr int kMinBlocks = kQ == 1 ? 2 : 1;
+    static constexpr int kWarps = kThreads / 32;
+    static constexpr int kQueue = kQ == 1 ? 128 : 64;             // survivors parked per warp
+    static constexpr int kKeys = kQ == 1 ? kTileKeys : kParamKeys;
+    static constexpr int kCountWords = kQ == 1 ? kTileRows : kQ * kTileRows / 2;  // batch: two 16-bit counts per word
+    static constexpr int kRowsPerThread = kTileRows / kThreads;
+    static constexpr int kGroup = kThreads / kQ;                  // threads that poll the predecessors of one query
+};
+
+template <int kQ>
+struct alignas(16) TileSmem {
+    using S = TileShape<kQ>;
+    unsigned char map[kMapEntries];        // first: zeroed with 16-byte stores
+    unsigned long long keys[kQ][S::kKeys];
+    unsigned long long part[S::kWarps];    // per-warp partial sums of the predecessors' totals
+    unsigned long long excl[kQ];           // hits of all earlier tiles
+    alignas(16) unsigned counts[S::kCountWords];   // zeroed with 16-byte stores
+    unsigned qe[S::kWarps][S::kQueue];     // parked survivors: arranged position relative to the tile's first unit
+    int mult[kQ][S::kKeys];
+    int n_keys[kQ];
+    unsigned warp_tot[kQ][S::kWarps];      // qualifying rows per warp, then their exclusive prefix
+    unsigned agg[kQ];
+    unsigned epoch, last;
+};
+
+struct TileArgs {
+    const unsigned short *fp;
     const VerifyRec *rec;
-    int *counts;
-    int n_keys;
+    const TileDesc *tiles;
+    TileDesc tail[kMaxTailTiles];           // the mutable tail's tiles, as they were when the query was enqueued
+    int n_tiles, tail_index;                // tiles >= tail_index belong to the tail; -1: none
+    const unsigned long long *keys_g;       // keys in global memory: a long single query, or the batch [n_queries][key_stride]
+    const int *mult_g;
+    const int *n_keys_g;                    // batch: distinct values per query
+    int key_stride, n_queries;
+    int n_keys;                             // single query
+    int min_match;
+    long long cap;
+    const int *vid;
+    const unsigned char *dead;
+    int *out;                               // [n_queries][out_stride]: {n_hits, overflow}, then (video_id, match_count)
+    long long out_stride;
+    long long *rows_out;                    // [cap] row index of every hit (single query; nullable)
+    long long *n_hits_out;                  // [n_queries]
+    unsigned long long *state;              // [n_tiles][kQ]: {query epoch << 32 | qualifying rows of the tile}
+    unsigned *ctrl;                         // {query epoch, finished CTAs}
+    const unsigned *my_flags;               // fused gather: this rank's flags, written by the peers
+    long long *trace;                       // debug: [n_tiles][8] phase timestamps (tvz_debug_tile_trace), normally null
+    GatherTargets gt;
 };
-
-// Verify one survivor: ONE memory round trip (value and row of the arranged position, fetched together
-// and already on their way to L2 since the survivor was parked), then the sorted query keys are
-// searched in shared memory and a real match adds into counts[row].
-__device__ __forceinline__ void fp_resolve(const FpCtx &cx, const FpSmem &sm, long long pos) {
-    const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(cx.rec + pos));
-    const unsigned long long v = (static_cast<unsigned long long>(r4.y) << 32) | r4.x;
-    const unsigned row = r4.z;
-    int lo = 0, hi = cx.n_keys;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (sm.keys[mid] < v) lo = mid + 1; else hi = mid;
-    }
-    if (lo >= cx.n_keys || sm.keys[lo] != v) return;  // fingerprint collision (or padding)
-    atomicAdd(&cx.counts[row], sm.mult[lo]);
-}
-
-// Verify the warp's parked survivors, 32 at a time (called by the whole warp).  Out of line for the
-// rare mid-stream call (a dense query filling the queue), inline for the one at the end of the stream.
-__device__ __forceinline__ void fp_drain_inline(const FpCtx &cx, const FpSmem &sm, const long long *qe, int n) {
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) fp_resolve(cx, sm, qe[i]);
-    __syncwarp();
-}
-__device__ __noinline__ void fp_drain(const FpCtx &cx, const FpSmem &sm, const long long *qe, int n) {
-    fp_drain_inline(cx, sm, qe, n);
-}
-
-constexpr int kFusedChunk = kFpThreads * kFusedRowsPerThread;   // rows per chunk of the count kernel's fused compaction
-
-template <bool kParamQuery>
-__global__ void __launch_bounds__(kFpThreads, TVZ_FP_MINB)
-match_count_kernel(const unsigned short *__restrict__ fp, long long n_units,
-                   const VerifyRec *__restrict__ rec,
-                   const unsigned long long *__restrict__ keys, const int *__restrict__ mult, int n_keys,
-                   int *__restrict__ counts, const __grid_constant__ SmallQuery sq,
-                   const __grid_constant__ FusedCompact fc) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FpSmem &sm = *reinterpret_cast<FpSmem *>(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // the first loads do not depend on the query: issue them before the byte map is built
-    const long long n_warps = static_cast<long long>(gridDim.x) * kFpWarps;
-    const long long wg = static_cast<long long>(blockIdx.x) * kFpWarps + warp;
-    const unsigned short *lane_fp = fp + lane * 16;
-    U32x8 v[kFpUnits];
-#pragma unroll
-    for (int j = 0; j < kFpUnits; ++j) {
-        const long long g = j * n_warps + wg;
-        if (g < n_units) v[j] = ld_stream_u32x8(lane_fp + g * kFpPerUnit);
-    }
-    for (int i = threadIdx.x; i < kMapEntries / 16; i += kFpThreads)
-        reinterpret_cast<uint4 *>(sm.map)[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_keys; i += kFpThreads) {
-        const unsigned long long k = kParamQuery ? sq.keys[i] : keys[i];
-        sm.keys[i] = k;
-        sm.mult[i] = kParamQuery ? sq.mult[i] : mult[i];
-        sm.map[filter_hash(k)] = 1;
-    }
-    __syncthreads();
-    pdl_wait();  // counts[] is being read and zeroed by the previous query's compaction until here
-    pdl_launch_dependents();  // only now: this query's compaction takes its tickets before ITS wait
-
-    const FpCtx cx{rec, counts, n_keys};
-    long long *qe = sm.qe[warp];
-    int queued = 0;  // warp-uniform, <= kFpQueue
-
-    for (long long g0 = wg; g0 < n_units; g0 += kFpUnits * n_warps) {
-#pragma unroll
-        for (int j = 0; j < kFpUnits; ++j) {
-            const long long g = g0 + j * n_warps;
-            if (g >= n_units) break;  // warp-uniform
-            unsigned flags = 0;       // bit k: the lane's k-th fingerprint is in the query's byte map
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const unsigned w = v[j].w[k];
-#ifdef TVZ_FP_NOLOOKUP   // tuning: streaming floor without the byte-map lookups
-                flags |= (w == 0x12345678u) << k;
-#else
-                flags |= static_cast<unsigned>(sm.map[w & 0xffffu]) << (2 * k);
-                flags |= static_cast<unsigned>(sm.map[w >> 16]) << (2 * k + 1);
-#endif
-            }
-#ifdef TVZ_FP_NOPARK     // tuning: lookups only, survivors dropped
-            if (flags == 0xdeadbeefu) qe[0] = 1;
-            flags = 0;
-#endif
-            // park the survivors' element indices, one per lane and round (a lane rarely holds two):
-            // slots from the vote mask, no atomics, no scan
-            unsigned mask = __ballot_sync(0xffffffffu, flags != 0u);
-            if (mask) {
-                const long long e0 = g * kFpPerUnit + lane * 16;
-                do {
-                    if (queued + __popc(mask) > kFpQueue) {
-                        fp_drain(cx, sm, qe, queued);
-                        queued = 0;
-                    }
-                    if (flags) {
-                        const long long e = e0 + (__ffs(flags) - 1);
-                        qe[queued + __popc(mask & ((1u << lane) - 1u))] = e;
-                        flags &= flags - 1;
-                        // what the verification will read, on its way to L2 while the stream goes on
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + e));
-                    }
-                    queued += __popc(mask);
-                    mask = __ballot_sync(0xffffffffu, flags != 0u);
-                } while (mask);
-            }
-            const long long gn = g + kFpUnits * n_warps;
-            if (gn < n_units) v[j] = ld_stream_u32x8(lane_fp + gn * kFpPerUnit);
-        }
-    }
-    fp_drain_inline(cx, sm, qe, queued);
-    if (fc.enabled) fused_compact<kFpThreads, false>(fc, counts, sm.mult);  // (the mult table is dead by now: scratch)
-}
-
-// ---- batched queries: up to 8 find_duplicates calls answered by ONE pass over the catalogue ----
-// (the reference runs one analysis thread per upload, app.py:43,472, each calling find_duplicates:
-// concurrent queries are the normal case).  The byte map holds one bit per query, so one LDS.U8
-// says which of the 8 queries might contain a value; survivors carry that mask through the
-// per-warp queue and add into counts[query][row].
-constexpr int kBatch = 8;
-struct alignas(16) BatchSmem {
-    unsigned char map[kMapEntries];
-    unsigned long long keys[kBatch][kParamKeys];
-    unsigned long long qv[kCountWarps][kWarpQueue];
-    long long qe[kCountWarps][kWarpQueue];            // value index | query mask << 56
-    int mult[kBatch][kParamKeys];
-    int n_keys[kBatch];
-};
-
-__global__ void __launch_bounds__(kCountThreads, 2)
-match_count_batch_kernel(const ulonglong2 *__restrict__ ts2, long long n_pairs_padded,
-                         const unsigned long long *__restrict__ keys, const int *__restrict__ mult,
-                         const int *__restrict__ n_keys, int n_batch, const long long *__restrict__ off,
-                         const int *__restrict__ block_row, long long n_rows, int *__restrict__ counts,
-                         long long counts_stride) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    BatchSmem &sm = *reinterpret_cast<BatchSmem *>(smem_raw);
-    pdl_wait();  // keys / n_keys are uploaded, counts[] zeroed by what runs before
-    pdl_launch_dependents();
-    for (int i = threadIdx.x; i < kMapEntries / 16; i += kCountThreads)
-        reinterpret_cast<uint4 *>(sm.map)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x < kBatch) sm.n_keys[threadIdx.x] = threadIdx.x < n_batch ? n_keys[threadIdx.x] : 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_batch * kParamKeys; i += kCountThreads) {
-        const int b = i / kParamKeys, k = i - b * kParamKeys;
-        if (k < sm.n_keys[b]) {
-            const unsigned long long key = keys[i];
-            sm.keys[b][k] = key;
-            sm.mult[b][k] = mult[i];
-            // byte-wide atomic OR through the containing 32-bit word
-            const uint32_t h = filter_hash(key);
-            atomicOr(reinterpret_cast<unsigned *>(sm.map) + (h >> 2), (1u << b) << (8 * (h & 3)));
-        }
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31;
-    unsigned long long *qv = sm.qv[threadIdx.x >> 5];
-    long long *qe = sm.qe[threadIdx.x >> 5];
-    int queued = 0;  // warp-uniform
-
-    auto resolve = [&](unsigned long long v, long long packed) {
-        const long long elem = packed & ((1ll << 56) - 1);
-        unsigned qmask = static_cast<unsigned>(static_cast<unsigned long long>(packed) >> 56);
-        long long row = -1;
-        while (qmask) {
-            const int b = __ffs(qmask) - 1;
-            qmask &= qmask - 1;
-            int lo = 0, hi = sm.n_keys[b];
-            const int nk = hi;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (sm.keys[b][mid] < v) lo = mid + 1; else hi = mid;
-            }
-            if (lo >= nk || sm.keys[b][lo] != v) continue;  // filter false positive for this query
-            if (row < 0) {
-                const long long blk = elem >> kBlockShift;
-                long long a = block_row[blk], z = block_row[blk + 1] + 1;
-                while (z - a > 1) {
-                    const long long mid = (a + z) >> 1;
-                    if (off[mid] <= elem) a = mid; else z = mid;
-                }
-                row = a;
-            }
-            atomicAdd(&counts[b * counts_stride + row], sm.mult[b][lo]);
-        }
-    };
-    auto drain = [&]() {
-        __syncwarp();
-        for (int i = lane; i < min(queued, kWarpQueue); i += 32) resolve(qv[i], qe[i]);
-        __syncwarp();
-        queued = 0;
-    };
-    auto park = [&](unsigned m, unsigned long long x, long long elem) {
-        const unsigned mask = __ballot_sync(0xffffffffu, m != 0);
-        if (m) {
-            const int slot = queued + __popc(mask & ((1u << lane) - 1u));
-            const long long packed = elem | (static_cast<long long>(m) << 56);
-            if (slot < kWarpQueue) { qv[slot] = x; qe[slot] = packed; }
-            else resolve(x, packed);
-        }
-        queued += __popc(mask);
-    };
-
-    constexpr int kUnits = kCountUnroll / 2;
-    const long long stride = static_cast<long long>(gridDim.x) * kChunkPairs;
-    long long base = static_cast<long long>(blockIdx.x) * kChunkPairs;
-    const U64x4 *ts4 = reinterpret_cast<const U64x4 *>(ts2);
-    U64x4 v[kUnits];
-    if (base < n_pairs_padded) {
-#pragma unroll
-        for (int j = 0; j < kUnits; ++j) v[j] = ld_stream_256(ts4 + (base >> 1) + unit_index(j));
-    }
-    for (; base < n_pairs_padded; base += stride) {
-        const bool more = base + stride < n_pairs_padded;
-        const U64x4 *next = ts4 + ((base + stride) >> 1);
-#pragma unroll
-        for (int j = 0; j < kUnits; ++j) {
-            const unsigned ma = sm.map[filter_hash(v[j].a)], mb = sm.map[filter_hash(v[j].b)];
-            const unsigned mc = sm.map[filter_hash(v[j].c)], md = sm.map[filter_hash(v[j].d)];
-            const unsigned any = __reduce_or_sync(0xffffffffu, (ma != 0) | ((mb != 0) << 1) | ((mc != 0) << 2) |
-                                                                   ((md != 0) << 3));
-            if (any) {
-                const long long elem = 2 * base + 4 * unit_index(j);
-                if (any & 1u) park(ma, v[j].a, elem);
-                if (any & 2u) park(mb, v[j].b, elem + 1);
-                if (any & 4u) park(mc, v[j].c, elem + 2);
-                if (any & 8u) park(md, v[j].d, elem + 3);
-                if (queued >= kWarpQueue / 2) drain();
-            }
-            if (more) v[j] = ld_stream_256(next + unit_index(j));
-        }
-    }
-    drain();
-}
-
-// Ordered compaction of the rows with counts[row] >= min_match, in ONE pass (decoupled
-// look-back): a block takes a ticket (so tickets start in order), counts its qualifying rows,
-// publishes {epoch, AGGREGATE, n}, sums its predecessors' records walking backwards 32 at a
-// time until it meets an inclusive PREFIX, publishes its own PREFIX, and writes its rows at
-// that offset in row order; counts[] is zeroed for the next query.  Records carry the query
-// epoch, so `state` never needs clearing.  out: int32 [cap+1][2]; out[0] = {n_hits saturated,
-// overflow flag}; out[1+h] = {video_id, match_count}; rows_out[h] = row index.
-constexpr unsigned long long kStateAggregate = 1ull << 32, kStatePrefix = 2ull << 32;
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
     unsigned long long v;
@@ -412,200 +172,322 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// kKeys (fragment mode, streaming kernel): the per-row input is a packed u64 best-candidate key
-// (common.cuh: frag_key) instead of counts[] + aux[]; score = key >> 32, the offset is decoded.
-template <bool kKeys>
-__global__ void __launch_bounds__(kScanThreads)
-match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, const int *__restrict__ vid,
-                     int *__restrict__ out, long long *__restrict__ rows_out, long long cap,
-                     long long *__restrict__ n_hits_out, unsigned long long *state, unsigned *ticket,
-                     const int *__restrict__ aux, int *__restrict__ aux_out, const __grid_constant__ GatherTargets gt,
-                     const BatchStrides bs, unsigned long long *__restrict__ keys) {
-    // batched queries: blockIdx.y picks the query, everything below is per query
-    counts += blockIdx.y * bs.counts;
-    out += blockIdx.y * bs.out;
-    rows_out += blockIdx.y * bs.rows;
-    state += blockIdx.y * bs.state;
-    ticket += blockIdx.y * 4;
-    n_hits_out += blockIdx.y;
-    // ticket[0] = next ticket, ticket[1] = query epoch.  The epoch is read BEFORE the ticket is
-    // taken and bumped by the holder of the last ticket, i.e. after every block has read it:
-    // the kernel is self-contained and can be replayed from a CUDA graph.
-    __shared__ unsigned s_block, s_epoch;
-    __shared__ long long s_excl;
-    __shared__ int ws[kScanThreads / 32];
-    // Tickets are taken BEFORE the dependency wait: ticket and epoch are only ever touched by compaction
-    // kernels, and the previous one has completed (the kernel in between waited for it before it let
-    // this one launch), so these two global round trips hide behind the count kernel's tail.
-    if (threadIdx.x == 0) {
-        unsigned e;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(ticket + 1) : "memory");
-        s_epoch = e;
-        s_block = atomicAdd(ticket, 1u);
-    }
-    pdl_launch_dependents();
-    pdl_wait();  // the count / fragment kernel before this one must have finished
-    __syncthreads();
-    const unsigned blk = s_block;
-    const unsigned epoch = s_epoch;
-    const unsigned long long tag = static_cast<unsigned long long>(epoch) << 34;
-    const long long r0 = blk * static_cast<long long>(kScanRowsPerBlock) + threadIdx.x * kScanRowsPerThread;
-    int cnt[kScanRowsPerThread];
-    int dec[kKeys ? kScanRowsPerThread : 1];
-    int mine = 0;
-    // the thread's 16 rows in 128-bit loads (the arrays are cudaMalloc-aligned, r0 is a multiple of 16);
-    // the last, partial thread range of a shard goes row by row
-    const bool whole = r0 + kScanRowsPerThread <= n_rows;
-    int cin[kKeys ? 1 : kScanRowsPerThread];
-    unsigned long long kin[kKeys ? kScanRowsPerThread : 1];
-    if (whole) {
-        if (kKeys) {
-#pragma unroll
-            for (int j = 0; j < kScanRowsPerThread; j += 2) {
-                const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(keys + r0 + j);
-                kin[j] = t.x;
-                kin[j + 1] = t.y;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < kScanRowsPerThread; j += 4) {
-                const int4 t = *reinterpret_cast<const int4 *>(counts + r0 + j);
-                cin[j] = t.x; cin[j + 1] = t.y; cin[j + 2] = t.z; cin[j + 3] = t.w;
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < kScanRowsPerThread; ++j) {
-        cnt[j] = -1;
-        if (whole || r0 + j < n_rows) {
-            int c;
-            if (kKeys) {
-                const unsigned long long k = whole ? kin[j] : keys[r0 + j];
-                if (k != 0) keys[r0 + j] = 0;
-                c = frag_key_score(k);
-                dec[j] = frag_key_delta(k);
-            } else {
-                c = whole ? cin[j] : counts[r0 + j];
-                if (c != 0) counts[r0 + j] = 0;
-            }
-            if (c >= min_match) { cnt[j] = c; ++mine; }
-        }
-    }
-    // block-wide exclusive scan of `mine` (rows are thread-contiguous: thread order = row order)
-    int incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int n = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((threadIdx.x & 31) >= d) incl += n;
-    }
-    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int w = lane < kScanThreads / 32 ? ws[lane] : 0;
-        int run = w;
-#pragma unroll
-        for (int d = 1; d < kScanThreads / 32; d <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, run, d);
-            if (lane >= d) run += n;
-        }
-        if (lane < kScanThreads / 32) ws[lane] = run - w;  // exclusive warp offsets
-        const unsigned agg = static_cast<unsigned>(__shfl_sync(0xffffffffu, run, kScanThreads / 32 - 1));
-        long long excl = 0;
-        if (blk == 0) {
-            if (lane == 0) st_release_u64(&state[0], tag | kStatePrefix | agg);
-        } else {
-            if (lane == 0) st_release_u64(&state[blk], tag | kStateAggregate | agg);
-            long long idx = static_cast<long long>(blk) - 1;
-            while (true) {
-                const long long i = idx - lane;
-                unsigned long long rec = 0;
-                unsigned prefix_mask, valid_mask;
-                do {  // poll until the window up to the first PREFIX is published for this epoch
-                    rec = i >= 0 ? ld_acquire_u64(&state[i]) : (tag | kStatePrefix);
-                    const bool ok = (rec >> 34) == epoch && ((rec >> 32) & 3ull) != 0;
-                    valid_mask = __ballot_sync(0xffffffffu, ok);
-                    prefix_mask = __ballot_sync(0xffffffffu, ok && ((rec >> 32) & 3ull) == 2ull);
-                    // lanes below the first PREFIX lane must all be valid
-                } while ((prefix_mask ? ((valid_mask | ~((prefix_mask & -prefix_mask) - 1u)) != 0xffffffffu)
-                                      : (valid_mask != 0xffffffffu)));
-                const unsigned upto = prefix_mask ? (prefix_mask & -prefix_mask) : 0u;
-                const unsigned take = prefix_mask ? ((upto - 1u) | upto) : 0xffffffffu;  // lanes 0..first PREFIX
-                long long v = ((take >> lane) & 1u) ? static_cast<long long>(rec & 0xffffffffull) : 0;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                excl += v;
-                if (prefix_mask) break;
-                idx -= 32;
-            }
-            // hits are bounded by rows < 2^32 per shard, so the running prefix fits 32 bits
-            if (lane == 0) st_release_u64(&state[blk], tag | kStatePrefix | static_cast<unsigned>(excl + agg));
-        }
-        if (lane == 0) {
-            s_excl = excl;
-            if (blk == gridDim.x - 1) {  // last ticket: every block has its ticket, totals are final
-                const long long total = excl + agg;
-                *n_hits_out = total;
-                out[0] = total > 0x7fffffffll ? 0x7fffffff : static_cast<int>(total);
-                out[1] = total > cap ? 1 : 0;
-                ticket[1] = (epoch + 1u) & 0x3fffffffu;  // every record is rewritten per query: no stale match
-                __threadfence();
-                ticket[0] = 0;
-            }
-        }
-    }
-    __syncthreads();
-    long long pos = s_excl + ws[threadIdx.x >> 5] + (incl - mine);
-#pragma unroll
-    for (int j = 0; j < kScanRowsPerThread; ++j) {
-        if (cnt[j] >= 0) {
-            if (pos < cap) {
-                out[2 + 2 * pos] = vid[r0 + j];
-                out[3 + 2 * pos] = cnt[j];
-                rows_out[pos] = r0 + j;
-                // per-row payload (fragment mode: best offset)
-                if (kKeys) aux_out[1 + pos] = dec[j];
-                else if (aux) aux_out[1 + pos] = aux[r0 + j];
-                // fused gather: every block ships its own hits to all peers (8-byte stores over NVLink)
-                for (int p = 0; p < gt.n_peers; ++p)
-                    *reinterpret_cast<int2 *>(gt.record[p] + 2 + 2 * pos) = make_int2(vid[r0 + j], cnt[j]);
-            }
-            ++pos;
-        }
-    }
-    if (gt.n_peers == 0) return;
-
-    // ---- fused gather epilogue: the block that finishes last publishes the header and the flag ----
-    __shared__ unsigned s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();  // this block's peer stores (and the local header) before it counts as done
-        const unsigned done = atomicAdd(ticket + 2, 1u);
-        s_last = done == gridDim.x - 1;
-        if (s_last) ticket[2] = 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    if (threadIdx.x < gt.n_peers) {
-        __threadfence_system();
-        const int2 hdr = make_int2(*reinterpret_cast<volatile int *>(out), *reinterpret_cast<volatile int *>(out + 1));
-        *reinterpret_cast<int2 *>(gt.record[threadIdx.x]) = hdr;  // {n_hits, overflow}
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gt.flag[threadIdx.x]), "r"(gt.epoch) : "memory");
+// The total of an earlier tile, once it is published for this query.  Bounded: a protocol bug must
+// surface as a launch failure, never as a hung GPU.  (Earlier tiles belong to CTAs with a lower
+// blockIdx, which the hardware dispatches first: a CTA never waits for one that is not running.)
+__device__ __forceinline__ unsigned wait_tile_total(const unsigned long long *p, unsigned epoch) {
+    unsigned polls = 0;
+    while (true) {
+        const unsigned long long r = ld_acquire_u64(p);
+        if (static_cast<unsigned>(r >> 32) == epoch) return static_cast<unsigned>(r);
+        if (++polls > 64) __nanosleep(64);
+        if (polls == (1u << 25)) __trap();
     }
 }
 
-// Wait until every peer's record for `epoch` has landed in this rank's gather buffer.  Bounded:
-// a peer that never answers turns into a launch failure, not a hung GPU.
-__global__ void gather_wait_kernel(const unsigned *flags, int n_peers, unsigned epoch) {
-    if (threadIdx.x >= n_peers) return;
-    unsigned v, polls = 0;
-    do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
-        if (v == epoch) return;
-        __nanosleep(64);
-    } while (++polls < (1u << 26));
-    __trap();
+template <class T>
+__device__ __forceinline__ int lower_bound_u64(const T &at, int n, unsigned long long v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (at(mid) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int kQ, bool kParamQuery>
+__global__ void __launch_bounds__(TileShape<kQ>::kThreads, TileShape<kQ>::kMinBlocks)
+match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ TileUnits tu,
+                  const __grid_constant__ SmallQuery sq) {
+    using S = TileShape<kQ>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem<kQ> &sm = *reinterpret_cast<TileSmem<kQ> *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int nq = kQ == 1 ? 1 : a.n_queries;
+    auto mark = [&](int k) {   // debug trace: slot 0 = global ns at CTA start, slots 1..7 = SM cycles at the phase ends
+        if (a.trace && tid == 0) {
+            long long t;
+            if (k == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            else t = clock64();
+            a.trace[static_cast<size_t>(tile) * 8 + k] = t;
+        }
+    };
+    mark(0);
+    mark(1);
+
+    // ---- prologue: nothing here depends on the previous kernel of the stream ----
+    unsigned unit_lo, unit_hi;
+    const bool in_tail = a.tail_index >= 0 && tile >= a.tail_index;
+    if (in_tail) { unit_lo = a.tail[tile - a.tail_index].unit_lo; unit_hi = a.tail[tile - a.tail_index].unit_hi; }
+    else if (tile < kMaxGridParam) { unit_lo = tu.lo[tile]; unit_hi = tu.hi[tile]; }
+    else { unit_lo = a.tiles[tile].unit_lo; unit_hi = a.tiles[tile].unit_hi; }
+    const bool resident = kQ > 1 || a.n_keys <= S::kKeys;   // the query's keys fit shared memory
+    const bool scan = kQ > 1 || a.n_keys > 0;               // an empty query matches nothing: no stream
+    if (!scan) unit_hi = unit_lo;
+    // the first loads do not depend on the query: issue them before the byte map is built
+    const unsigned short *lane_fp = a.fp + lane * 16;
+    U32x8 v[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const unsigned g = unit_lo + warp + j * S::kWarps;
+        if (g < unit_hi) v[j] = ld_stream_u32x8(lane_fp + static_cast<size_t>(g) * kFpPerUnit);
+    }
+    TileDesc td;
+    if (in_tail) td = a.tail[tile - a.tail_index];
+    else td = a.tiles[tile];
+    for (int i = tid; i < kMapEntries / 16; i += S::kThreads)
+        reinterpret_cast<uint4 *>(sm.map)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < S::kCountWords / 4; i += S::kThreads)
+        reinterpret_cast<uint4 *>(sm.counts)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (kQ > 1 && tid < kQ) sm.n_keys[tid] = tid < nq ? min(a.n_keys_g[tid], S::kKeys) : 0;
+    __syncthreads();
+    if (kQ == 1) {
+        for (int i = tid; i < a.n_keys; i += S::kThreads) {
+            const unsigned long long k = kParamQuery ? sq.keys[i] : a.keys_g[i];
+            if (resident) {
+                sm.keys[0][i] = k;
+                sm.mult[0][i] = kParamQuery ? sq.mult[i] : a.mult_g[i];
+            }
+            sm.map[filter_hash(k)] = 1;
+        }
+    } else {
+        for (int i = tid; i < nq * a.key_stride; i += S::kThreads) {
+            const int b = i / a.key_stride, k = i - b * a.key_stride;
+            if (k < sm.n_keys[b]) {
+                const unsigned long long key = a.keys_g[i];
+                sm.keys[b][k] = key;
+                sm.mult[b][k] = a.mult_g[i];
+                const uint32_t h = filter_hash(key);   // byte-wide OR through the containing 32-bit word
+                atomicOr(reinterpret_cast<unsigned *>(sm.map) + (h >> 2), (1u << b) << (8 * (h & 3)));
+            }
+        }
+    }
+    // the compaction will read the video ids of this tile's rows: on their way to L2 now
+    if (tid * 32 < td.n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vid + td.row_lo + tid * 32));
+    __syncthreads();
+    mark(2);
+    pdl_wait();               // the previous query on this workspace still owns state / ctrl / out until here
+    pdl_launch_dependents();  // the next kernel may run its own prologue while this one streams
+    if (tid == 0) {
+        unsigned e;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(a.ctrl) : "memory");
+        sm.epoch = e;
+    }
+    mark(3);
+
+    // ---- stream the tile's fingerprints; survivors are parked per warp and verified at the end ----
+    const long long pos0 = static_cast<long long>(unit_lo) * kFpPerUnit;
+    auto resolve = [&](unsigned rel) {
+        const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(a.rec + pos0 + rel));
+        const unsigned long long val = (static_cast<unsigned long long>(r4.y) << 32) | r4.x;
+        const unsigned local = r4.z - static_cast<unsigned>(td.row_lo);
+        if (local >= static_cast<unsigned>(td.n_rows)) return;   // a neighbour's row in a shared boundary unit
+        if (kQ == 1) {
+            int m;
+            if (resident) {
+                const int lo = lower_bound_u64([&](int i) { return sm.keys[0][i]; }, a.n_keys, val);
+                if (lo >= a.n_keys || sm.keys[0][lo] != val) return;   // fingerprint collision (or padding)
+                m = sm.mult[0][lo];
+            } else {
+                const int lo = lower_bound_u64([&](int i) { return __ldg(a.keys_g + i); }, a.n_keys, val);
+                if (lo >= a.n_keys || __ldg(a.keys_g + lo) != val) return;
+                m = __ldg(a.mult_g + lo);
+            }
+            atomicAdd(&sm.counts[local], static_cast<unsigned>(m));
+        } else {
+            unsigned qm = sm.map[filter_hash(val)];
+            while (qm) {
+                const int b = __ffs(qm) - 1;
+                qm &= qm - 1;
+                const int nk = sm.n_keys[b];
+                const int lo = lower_bound_u64([&](int i) { return sm.keys[b][i]; }, nk, val);
+                if (lo >= nk || sm.keys[b][lo] != val) continue;       // filter false positive for this query
+                atomicAdd(&sm.counts[b * (kTileRows / 2) + (local >> 1)],
+                          static_cast<unsigned>(sm.mult[b][lo]) << (16 * (local & 1)));
+            }
+        }
+    };
+    unsigned *qe = sm.qe[warp];
+    int queued = 0;  // warp-uniform, <= kQueue
+    auto drain = [&]() {
+        __syncwarp();
+        for (int i = lane; i < queued; i += 32) resolve(qe[i]);
+        __syncwarp();
+        queued = 0;
+    };
+    for (unsigned g0 = unit_lo + warp; g0 < unit_hi; g0 += 2 * S::kWarps) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const unsigned g = g0 + j * S::kWarps;
+            if (g >= unit_hi) break;  // warp-uniform
+            unsigned flags = 0;       // bit k: the lane's k-th fingerprint is in the byte map
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const unsigned w = v[j].w[k];
+                if (kQ == 1) {   // the map holds 0 / 1
+                    flags |= static_cast<unsigned>(sm.map[w & 0xffffu]) << (2 * k);
+                    flags |= static_cast<unsigned>(sm.map[w >> 16]) << (2 * k + 1);
+                } else {         // ... or one bit per query
+                    flags |= static_cast<unsigned>(sm.map[w & 0xffffu] != 0) << (2 * k);
+                    flags |= static_cast<unsigned>(sm.map[w >> 16] != 0) << (2 * k + 1);
+                }
+            }
+            // park the survivors' positions, one per lane and round (a lane rarely holds two):
+            // slots from the vote mask, no atomics, no scan
+            unsigned mask = __ballot_sync(0xffffffffu, flags != 0u);
+            if (mask) {
+                const unsigned e0 = (g - unit_lo) * kFpPerUnit + lane * 16;
+                do {
+                    if (queued + __popc(mask) > S::kQueue) drain();
+                    if (flags) {
+                        const unsigned e = e0 + (__ffs(flags) - 1);
+                        qe[queued + __popc(mask & ((1u << lane) - 1u))] = e;
+                        flags &= flags - 1;
+                        // what the verification will read, on its way to L2 while the stream goes on
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rec + pos0 + e));
+                    }
+                    queued += __popc(mask);
+                    mask = __ballot_sync(0xffffffffu, flags != 0u);
+                } while (mask);
+            }
+            const unsigned gn = g + 2 * S::kWarps;
+            if (gn < unit_hi) v[j] = ld_stream_u32x8(lane_fp + static_cast<size_t>(gn) * kFpPerUnit);
+        }
+    }
+    mark(4);
+    drain();
+    __syncthreads();   // every count of this tile is final; sm.epoch is visible
+    mark(5);
+
+    // ---- compaction of the tile's own rows ----
+    const unsigned epoch = sm.epoch;
+    const int r0 = tid * S::kRowsPerThread;
+    const bool want_all = a.min_match <= 0;   // then rows without any match qualify too -- except replaced ones
+    auto count_of = [&](int b, int local) -> int {
+        if (kQ == 1) return static_cast<int>(sm.counts[local]);
+        return static_cast<int>((sm.counts[b * (kTileRows / 2) + (local >> 1)] >> (16 * (local & 1))) & 0xffffu);
+    };
+    auto qualifies = [&](int c, int local) -> bool {
+        if (local >= td.n_rows || c < a.min_match) return false;
+        return !(want_all && a.dead && a.dead[td.row_lo + local]);
+    };
+    for (int b = 0; b < nq; ++b) {
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < S::kRowsPerThread; ++j) mine += qualifies(count_of(b, r0 + j), r0 + j);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0) sm.warp_tot[b][warp] = mine;
+    }
+    __syncthreads();
+    if (warp < nq) {   // warp b: exclusive prefix of the warps' totals of query b; publish the tile's total
+        const int b = warp;
+        const unsigned w = lane < S::kWarps ? sm.warp_tot[b][lane] : 0u;
+        unsigned incl = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane < S::kWarps) sm.warp_tot[b][lane] = incl - w;
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) {
+            sm.agg[b] = total;
+            st_release_u64(&a.state[static_cast<size_t>(tile) * kQ + b], (static_cast<unsigned long long>(epoch) << 32) | total);
+        }
+    }
+    {   // hits of all earlier tiles: every thread polls its share of the predecessors -- one round trip
+        const int b = tid / S::kGroup, i0 = tid - b * S::kGroup;
+        unsigned long long sum = 0;
+        if (b < nq)
+            for (int i = i0; i < tile; i += S::kGroup) sum += wait_tile_total(&a.state[static_cast<size_t>(i) * kQ + b], epoch);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) sm.part[warp] = sum;
+    }
+    __syncthreads();
+    mark(6);
+    if (tid < nq) {
+        constexpr int kWarpsPerGroup = S::kGroup / 32;
+        unsigned long long e = 0;
+        for (int w = 0; w < kWarpsPerGroup; ++w) e += sm.part[tid * kWarpsPerGroup + w];
+        sm.excl[tid] = e;
+        if (tile == a.n_tiles - 1) {   // the last tile knows every query's total
+            const long long total = static_cast<long long>(e) + sm.agg[tid];
+            a.n_hits_out[tid] = total;
+            int *o = a.out + tid * a.out_stride;
+            o[0] = total > 0x7fffffffll ? 0x7fffffff : static_cast<int>(total);
+            o[1] = total > a.cap ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    for (int b = 0; b < nq; ++b) {
+        int cnt[S::kRowsPerThread];
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < S::kRowsPerThread; ++j) {
+            cnt[j] = count_of(b, r0 + j);
+            if (qualifies(cnt[j], r0 + j)) ++mine; else cnt[j] = -1;   // counts are never negative
+        }
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        long long pos = static_cast<long long>(sm.excl[b]) + sm.warp_tot[b][warp] + (incl - mine);
+        int *o = a.out + b * a.out_stride;
+#pragma unroll
+        for (int j = 0; j < S::kRowsPerThread; ++j) {
+            if (cnt[j] >= 0) {
+                if (pos < a.cap) {
+                    const int row = td.row_lo + r0 + j;
+                    const int2 hit = make_int2(a.vid[row], cnt[j]);
+                    *reinterpret_cast<int2 *>(o + 2 + 2 * pos) = hit;
+                    if (kQ == 1 && a.rows_out) a.rows_out[pos] = row;
+                    // fused gather: every CTA ships its own hits to all peers (8-byte stores over NVLink)
+                    for (int p = 0; p < a.gt.n_peers; ++p)
+                        *reinterpret_cast<int2 *>(a.gt.record[p] + b * a.gt.query_stride + 2 + 2 * pos) = hit;
+                }
+                ++pos;
+            }
+        }
+    }
+
+    // ---- the CTA that finishes last starts the next epoch (and completes the fused gather) ----
+    __syncthreads();
+    mark(7);
+    if (tid == 0) {
+        if (a.gt.n_peers) __threadfence_system();  // this CTA's peer stores (and the local header) before it counts as done
+        else __threadfence();
+        const unsigned done = atomicAdd(a.ctrl + 1, 1u);
+        sm.last = done == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!sm.last) return;
+    if (tid == 0) {
+        a.ctrl[1] = 0;
+        a.ctrl[0] = epoch + 1u ? epoch + 1u : 1u;   // state[] starts zeroed: epoch 0 is never used
+    }
+    if (a.gt.n_peers == 0) return;
+    if (tid < a.gt.n_peers) {
+        __threadfence_system();
+        for (int b = 0; b < nq; ++b) {
+            const volatile int *o = a.out + b * a.out_stride;
+            *reinterpret_cast<int2 *>(a.gt.record[tid] + b * a.gt.query_stride) = make_int2(o[0], o[1]);  // {n_hits, overflow}
+        }
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.gt.flag[tid]), "r"(a.gt.epoch) : "memory");
+        // ... and wait until every peer's record for this epoch has landed here (bounded, see above)
+        unsigned f, polls = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(a.my_flags + tid) : "memory");
+            if (f == a.gt.epoch) break;
+            __nanosleep(64);
+            if (++polls == (1u << 26)) __trap();
+        } while (true);
+    }
 }
 
 // Per hit row: the 1-based query index at which the row reaches min_match.
@@ -637,82 +519,110 @@ __global__ void match_kth_kernel(const unsigned long long *__restrict__ ts, cons
     }
 }
 
+// Row upsert on the device (db.py:43-64): neutralise the replaced row, append the new one to the tail.
+struct UpsertArgs {
+    VerifyRec *rec;
+    unsigned short *fp;
+    unsigned long long *ts;
+    long long *off;
+    int *vid;
+    unsigned char *dead;
+    long long kill_row;                    // -1: nothing to replace
+    long long kill_pos_lo, kill_pos_hi;    // arranged positions that may hold the replaced row's records
+    long long kill_ts_lo, kill_ts_hi;      // its values in row order
+    long long new_row, pos0, ts0;          // where the new row goes: arranged position (tail: identity order) and row-order position
+    int new_vid, n;
+    const unsigned long long *vals_g;      // n > kParamKeys: values staged in device memory
+    unsigned long long vals[kParamKeys];
+};
+__global__ void __launch_bounds__(512) upsert_kernel(const __grid_constant__ UpsertArgs u) {
+    if (u.kill_row >= 0) {
+        for (long long p = u.kill_pos_lo + threadIdx.x; p < u.kill_pos_hi; p += blockDim.x)
+            if (u.rec[p].row == static_cast<unsigned>(u.kill_row)) u.rec[p].ts = kPadPattern;
+        for (long long p = u.kill_ts_lo + threadIdx.x; p < u.kill_ts_hi; p += blockDim.x) u.ts[p] = kPadPattern;
+        if (threadIdx.x == 0 && u.kill_row != u.new_row) u.dead[u.kill_row] = 1;
+    }
+    __syncthreads();   // a row rewritten in place: its old records are gone before the new ones land
+    for (int i = threadIdx.x; i < u.n; i += blockDim.x) {
+        const unsigned long long v = u.vals_g ? u.vals_g[i] : u.vals[i];
+        VerifyRec r;
+        r.ts = v;
+        r.row = static_cast<unsigned>(u.new_row);
+        r.pad = 0;
+        u.rec[u.pos0 + i] = r;
+        u.fp[u.pos0 + i] = static_cast<unsigned short>(filter_hash(v));
+        u.ts[u.ts0 + i] = v;
+    }
+    if (threadIdx.x == 0) {
+        u.off[u.new_row] = u.ts0;
+        u.off[u.new_row + 1] = u.ts0 + u.n;
+        u.vid[u.new_row] = u.new_vid;
+        u.dead[u.new_row] = 0;
+    }
+}
+
 }  // namespace
-
-int compact_blocks(long long n_rows) {
-    return static_cast<int>((n_rows + kScanRowsPerBlock - 1) / kScanRowsPerBlock);
-}
-
-// Ordered compaction of counts[row] >= min_match (see match_compact_kernel).  `state` holds
-// compact_blocks(n_rows) u64 records (zero-initialised once), `ticket` two u32 {0, 1}.
-int compact_enqueue(int *counts, long long n_rows, int min_match, const int *vid, int *out, long long *rows_out,
-                    long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket,
-                    const int *aux, int *aux_out, cudaStream_t st, const GatherTargets *gather) {
-    const GatherTargets none{};
-    TVZ_CUDA(launch_pdl(match_compact_kernel<false>, dim3(compact_blocks(n_rows)), dim3(kScanThreads), 0, st, false, counts,
-                        n_rows, min_match, vid, out, rows_out, cap, n_hits_out, state, ticket, aux, aux_out,
-                        gather ? *gather : none, BatchStrides{}, static_cast<unsigned long long *>(nullptr)));
-    return TVZ_OK;
-}
-
-// Same compaction over packed best-candidate keys (fragment streaming kernel); keys[] is zeroed.
-int compact_enqueue_keys(unsigned long long *keys, long long n_rows, int min_match, const int *vid, int *out,
-                         long long *rows_out, long long cap, long long *n_hits_out, unsigned long long *state,
-                         unsigned *ticket, int *delta_out, cudaStream_t st) {
-    TVZ_CUDA(launch_pdl(match_compact_kernel<true>, dim3(compact_blocks(n_rows)), dim3(kScanThreads), 0, st, false,
-                        static_cast<int *>(nullptr), n_rows, min_match, vid, out, rows_out, cap, n_hits_out, state, ticket,
-                        static_cast<const int *>(nullptr), delta_out, GatherTargets{}, BatchStrides{}, keys));
-    return TVZ_OK;
-}
-
-int compact_enqueue_batch(int *counts, long long n_rows, int min_match, const int *vid, int *out, long long *rows_out,
-                          long long cap, long long *n_hits_out, unsigned long long *state, unsigned *ticket, int n_batch,
-                          const BatchStrides &bs, cudaStream_t st) {
-    const GatherTargets none{};
-    dim3 grid(compact_blocks(n_rows), n_batch);
-    TVZ_CUDA(launch_pdl(match_compact_kernel<false>, grid, dim3(kScanThreads), 0, st, false, counts, n_rows, min_match, vid, out,
-                        rows_out, cap, n_hits_out, state, ticket, static_cast<const int *>(nullptr),
-                        static_cast<int *>(nullptr), none, bs, static_cast<unsigned long long *>(nullptr)));
-    return TVZ_OK;
-}
-
-int gather_wait_enqueue(const unsigned *d_flags, int n_peers, unsigned epoch, cudaStream_t st) {
-    gather_wait_kernel<<<1, 32, 0, st>>>(d_flags, n_peers, epoch);
-    TVZ_CUDA(cudaGetLastError());
-    return TVZ_OK;
-}
-
 }  // namespace tvz
 
 using namespace tvz;
 
+struct TailRow {
+    int vid;
+    long long start;   // first value, relative to the tail
+    int n;
+    bool alive;
+};
+
 struct tvz_catalog {
     int device = 0;
-    long long n_rows = 0, n_vals = 0, n_pairs = 0;
-    long long n_pairs_padded = 0;  // ts is padded with a NaN pattern to whole count-kernel chunks
+    long long n_rows_main = 0, n_vals_main = 0;
+    long long n_units_main = 0;              // fingerprint units of the packed part
+    long long ts_main_padded = 0;            // row-order values of the packed part (+ padding); the tail follows
+    unsigned short *d_fp = nullptr;          // filter_hash of every stored value, padded to whole 512-value units and
+                                             // arranged inside each unit for conflict-free lookups (arrange_fingerprints)
+    VerifyRec *d_rec = nullptr;              // the value behind d_fp[p] and its row, in the same arranged order
     unsigned long long *d_ts = nullptr;
-    unsigned short *d_fp = nullptr;  // filter_hash of every stored value, padded to whole 512-value units and
-                                     // arranged inside each unit for conflict-free lookups (arrange_fingerprints)
-    void *d_rec = nullptr;           // VerifyRec[p]: the value behind d_fp[p] and its row, in the same arranged order
-    long long n_units = 0;
     long long *d_off = nullptr;
     int *d_vid = nullptr;
-    int *d_block_row = nullptr;    // row holding stored value b*1024 (coarse index for hit -> row)
+    unsigned char *d_dead = nullptr;
+    TileDesc *d_tiles = nullptr;
+    std::vector<TileDesc> tiles;             // tiles of the packed rows
+    TileUnits units{};
+    int tail_index = -1;
+    // ---- mutable tail (tvz_catalog_upsert); everything below is guarded by `mu` ----
+    mutable std::mutex mu;
+    long long tail_cap_vals = 0;             // 0: immutable catalogue
+    long long tail_used_vals = 0;
+    int tail_used_rows = 0;
+    std::vector<TailRow> tail_rows;
+    std::vector<unsigned long long> tail_vals;        // host mirror of the tail's values (tail compaction)
+    std::vector<long long> h_off;                     // packed rows: where a replaced row's values live
+    std::unordered_map<int, long long> row_of_vid;    // first live row of a video (db.py:47 .first()); built on first upsert
+    bool row_map_built = false;
+    long long dead_main = 0;
+    cudaStream_t mut_stream = nullptr;
+    cudaEvent_t mut_event = nullptr;
+    std::atomic<unsigned long long> mut_seq{0};
+    unsigned long long *d_stage = nullptr;   // long rows: values staged for the upsert kernel
+    unsigned long long *h_stage = nullptr;   // pinned
+    long long stage_cap = 0;
+
+    long long n_rows() const { return n_rows_main + tail_used_rows; }
+    int tail_tiles() const { return tail_index < 0 ? 0 : std::max(1, (tail_used_rows + kTileRows - 1) / kTileRows); }
+    long long n_tiles() const { return static_cast<long long>(tiles.size()) + tail_tiles(); }
+    long long max_tiles() const { return static_cast<long long>(tiles.size()) + (tail_index < 0 ? 0 : kMaxTailTiles); }
 };
 
 struct tvz_match_ws {
     const tvz_catalog *cat = nullptr;
     long long cap = 0;
-    int n_blocks = 0;
-    int *d_counts = nullptr;       // [n_rows], zero between queries
-    unsigned long long *d_state = nullptr;  // [n_blocks] look-back records {epoch, flag, value}
-    unsigned *d_ticket = nullptr;           // {next ticket, query epoch}
-    int *d_out = nullptr;          // [cap+1][2]
-    long long *d_rows = nullptr;   // [cap]
-    int *d_kth = nullptr;          // [cap]
-    long long *d_nhits = nullptr;  // [1]
-    unsigned *d_chunk_hits = nullptr;  // [n_rows / 4096 + 1] fused compaction: qualifying rows per chunk
-    // query staging: keys u64 [kMaxKeys] | q_canon u64 [q_cap] | mult i32 [kMaxKeys]
+    unsigned long long *d_state = nullptr;  // [n_tiles][kBatch] tile totals {epoch, count}
+    unsigned *d_ctrl = nullptr;             // {query epoch, finished CTAs}
+    int *d_out = nullptr;                   // [cap+1][2]
+    long long *d_rows = nullptr;            // [cap]
+    int *d_kth = nullptr;                   // [cap]
+    long long *d_nhits = nullptr;           // [kBatch]
+    // query staging: q_canon u64 [q_cap] | keys u64 [q_cap] | mult i32 [q_cap]
     unsigned long long *d_keys = nullptr, *d_qcanon = nullptr;
     int *d_mult = nullptr;
     uint8_t *h_stage = nullptr;    // pinned
@@ -720,22 +630,30 @@ struct tvz_match_ws {
     int q_cap = 0;
     int *h_out = nullptr;          // pinned [cap+1][2]
     int *h_kth = nullptr;          // pinned [cap]
-    cudaStream_t stream = nullptr; // private stream for the synchronous entry point
+    cudaStream_t stream = nullptr; // private stream for the synchronous entry points
     cudaEvent_t staged = nullptr;  // the pinned staging buffer has been consumed
     bool stage_busy = false;
-    bool timing = false;           // debug: bracket the count kernel(s) with events
+    bool timing = false;           // debug: bracket the kernel with events
     cudaEvent_t t0 = nullptr, t1 = nullptr;
-    // batched queries (allocated on first use): per-query copies of counts/out/rows/state/ticket
-    int *b_counts = nullptr, *b_out = nullptr, *b_mult = nullptr, *b_nkeys = nullptr;
-    long long *b_rows = nullptr, *b_nhits = nullptr;
-    unsigned long long *b_state = nullptr, *b_keys = nullptr;
-    unsigned *b_ticket = nullptr;
-    uint8_t *hb_stage = nullptr;   // pinned: keys | mult | n_keys
-    int *hb_out = nullptr;         // pinned [8][cap+1][2]
-    long long hb_cap = 0;
+    long long *d_trace = nullptr;           // debug (not owned)
+    unsigned long long seen_mut = 0;        // last catalogue mutation a stream of this workspace has waited for
+    cudaStream_t seen_stream = nullptr;     // ... and which stream that was
+    // batched queries (allocated on first use)
+    int *b_out = nullptr;                   // [kBatch][cap+1][2]
+    uint8_t *b_dev = nullptr;               // keys u64 [kBatch][kParamKeys] | mult i32 [..] | n_keys i32 [kBatch]
+    uint8_t *hb_stage = nullptr;            // pinned: kStageSlots mirrors of b_dev, used round-robin
+    cudaEvent_t b_staged[4] = {};           // slot i has been copied to the device
+    bool b_stage_busy[4] = {};
+    int b_slot = 0;
+    int *hb_out = nullptr;                  // pinned [kBatch][cap+1][2]
 };
 
 namespace {
+
+constexpr size_t kBatchKeysBytes = static_cast<size_t>(kBatch) * kParamKeys * 8;
+constexpr size_t kBatchMultBytes = static_cast<size_t>(kBatch) * kParamKeys * 4;
+constexpr size_t kBatchStageBytes = (kBatchKeysBytes + kBatchMultBytes + kBatch * 4 + 63) / 64 * 64;
+constexpr int kStageSlots = 4;   // pinned staging slots: the host prepares batch k+1..k+3 while batch k still waits for its copy
 
 inline unsigned long long canon_bits(double v) {
     unsigned long long b;
@@ -745,6 +663,27 @@ inline unsigned long long canon_bits(double v) {
 }
 inline bool is_nan_bits(unsigned long long b) {
     return (b & 0x7ff0000000000000ull) == 0x7ff0000000000000ull && (b & 0x000fffffffffffffull) != 0;
+}
+
+// One row's stored form: NaN dropped, -0.0 folded, in-row repeats dropped (first occurrence kept).
+void canon_row(const double *v, long long n, std::vector<unsigned long long> &out, std::unordered_set<unsigned long long> &seen) {
+    const size_t start = out.size();
+    bool ascending = true;
+    double last = 0;
+    for (long long j = 0; j < n; ++j) {
+        const unsigned long long b = canon_bits(v[j]);
+        if (is_nan_bits(b)) continue;
+        if (out.size() > start && !(v[j] > last)) ascending = false;
+        last = v[j];
+        out.push_back(b);
+    }
+    if (!ascending) {  // rare: unsorted or repeated values -> stable de-duplication
+        seen.clear();
+        size_t w = start;
+        for (size_t j = start; j < out.size(); ++j)
+            if (seen.insert(out[j]).second) out[w++] = out[j];
+        out.resize(w);
+    }
 }
 
 // Fingerprints of one 512-value unit, ARRANGED so that the k-th lookups of the 32 lanes (positions
@@ -796,252 +735,147 @@ void arrange_fingerprints(const unsigned long long *ts, long long n_vals, long l
     }
 }
 
+// Cut rows [0, n_rows) into tiles of whole rows: at most kTileRows rows each, about the same number of
+// stored values each, about `want` tiles (one wave of CTAs; a multiple of it when rows are short).
+void build_tiles(const std::vector<long long> &off, long long n_rows, int want, std::vector<TileDesc> &tiles) {
+    tiles.clear();
+    if (n_rows <= 0) return;
+    const long long n_vals = off[n_rows];
+    const long long by_rows = (n_rows + kTileRows - 1) / kTileRows;
+    const long long waves = std::max<long long>(1, (by_rows + want - 1) / want);
+    const long long target = std::max<long long>(static_cast<long long>(kMinTileUnits) * kFpPerUnit,
+                                                 (n_vals + waves * want - 1) / (waves * want));
+    long long r = 0;
+    while (r < n_rows) {
+        // first row index e with off[e] - off[r] >= target
+        long long e = std::lower_bound(off.begin() + r, off.begin() + n_rows + 1, off[r] + target) - off.begin();
+        e = std::min<long long>({e, r + kTileRows, n_rows});
+        if (e <= r) e = r + 1;
+        if (n_rows - e < kTileRows / 8 && n_rows - r <= kTileRows && off[n_rows] - off[r] < target + target / 4) e = n_rows;  // no sliver at the end
+        TileDesc t;
+        t.row_lo = static_cast<int>(r);
+        t.n_rows = static_cast<int>(e - r);
+        t.unit_lo = static_cast<unsigned>(off[r] / kFpPerUnit);
+        t.unit_hi = off[e] == off[r] ? t.unit_lo : static_cast<unsigned>((off[e] + kFpPerUnit - 1) / kFpPerUnit);
+        tiles.push_back(t);
+        r = e;
+    }
+}
+
+void fill_units(tvz_catalog *c) {
+    for (size_t t = 0; t < c->tiles.size() && t < static_cast<size_t>(kMaxGridParam); ++t) {
+        c->units.lo[t] = c->tiles[t].unit_lo;
+        c->units.hi[t] = c->tiles[t].unit_hi;
+    }
+}
+
+// Tail tile k holds tail rows [k * 4096, (k + 1) * 4096) and the units their values span (tail rows are
+// contiguous in append order).  Called with the lock held.
+void tail_descs(const tvz_catalog *c, TileDesc *out) {
+    const int nt = c->tail_tiles();
+    for (int k = 0; k < nt; ++k) {
+        const int r0 = k * kTileRows, r1 = std::min(c->tail_used_rows, r0 + kTileRows);
+        TileDesc t;
+        t.row_lo = static_cast<int>(c->n_rows_main) + r0;
+        t.n_rows = std::max(0, r1 - r0);
+        const long long v0 = r1 > r0 ? c->tail_rows[r0].start : 0;
+        const long long v1 = r1 > r0 ? c->tail_rows[r1 - 1].start + c->tail_rows[r1 - 1].n : 0;
+        t.unit_lo = static_cast<unsigned>(c->n_units_main + v0 / kFpPerUnit);
+        t.unit_hi = v1 > v0 ? static_cast<unsigned>(c->n_units_main + (v1 + kFpPerUnit - 1) / kFpPerUnit) : t.unit_lo;
+        out[k] = t;
+    }
+}
+
 int ensure_query_capacity(tvz_match_ws *ws, int qn) {
     if (qn <= ws->q_cap) return TVZ_OK;
     int cap = std::max(256, ws->q_cap);
     while (cap < qn) cap *= 2;
     if (ws->stage_busy) { TVZ_CUDA(cudaEventSynchronize(ws->staged)); ws->stage_busy = false; }
     if (ws->d_qcanon) cudaFree(ws->d_qcanon);
+    if (ws->d_mult) cudaFree(ws->d_mult);
     if (ws->h_stage) cudaFreeHost(ws->h_stage);
     ws->d_qcanon = nullptr;
+    ws->d_keys = nullptr;
+    ws->d_mult = nullptr;
     ws->h_stage = nullptr;
     ws->q_cap = 0;
-    TVZ_CUDA(cudaMalloc(&ws->d_qcanon, sizeof(unsigned long long) * cap));
-    // staging holds, per launch chunk, keys+mult, and once the canonical query
+    TVZ_CUDA(cudaMalloc(&ws->d_qcanon, sizeof(unsigned long long) * cap * 2));  // canonical query, then sorted keys
+    ws->d_keys = ws->d_qcanon + cap;
+    TVZ_CUDA(cudaMalloc(&ws->d_mult, sizeof(int) * cap));
     ws->stage_bytes = sizeof(unsigned long long) * cap * 2 + sizeof(int) * cap + 64;
     TVZ_CUDA(cudaHostAlloc(&ws->h_stage, ws->stage_bytes, cudaHostAllocDefault));
     ws->q_cap = cap;
     return TVZ_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_video_id, int64_t n_rows,
-                       tvz_catalog **out) {
-    return guarded([&]() -> int {
-    TVZ_REQUIRE(out, "null out pointer");
-    *out = nullptr;
-    TVZ_REQUIRE(n_rows >= 0, "negative n_rows");
-    TVZ_REQUIRE(n_rows == 0 || (h_off && h_video_id), "null offsets/video ids");
-    TVZ_REQUIRE(n_rows == 0 || h_off[0] == 0, "offsets must start at 0");
-    for (int64_t r = 0; r < n_rows; ++r)
-        TVZ_REQUIRE(h_off[r + 1] >= h_off[r], "offsets must be non-decreasing (row %lld)", (long long)r);
-    const int64_t n_in = n_rows ? h_off[n_rows] : 0;
-    TVZ_REQUIRE(n_in == 0 || h_ts, "null timestamps");
-
-    // canonicalise: drop NaN, fold -0.0, drop in-row repeats (first occurrence kept)
-    std::vector<unsigned long long> ts;
-    ts.reserve(static_cast<size_t>(n_in) + 2);
-    std::vector<long long> off(static_cast<size_t>(n_rows) + 1, 0);
-    std::unordered_set<unsigned long long> seen;
-    for (int64_t r = 0; r < n_rows; ++r) {
-        const size_t start = ts.size();
-        bool ascending = true;
-        double last = 0;
-        for (int64_t j = h_off[r]; j < h_off[r + 1]; ++j) {
-            const double v = h_ts[j];
-            const unsigned long long b = canon_bits(v);
-            if (is_nan_bits(b)) continue;
-            if (ts.size() > start && !(v > last)) ascending = false;
-            last = v;
-            ts.push_back(b);
-        }
-        if (!ascending) {  // rare: unsorted or repeated values -> stable de-duplication
-            seen.clear();
-            size_t w = start;
-            for (size_t j = start; j < ts.size(); ++j)
-                if (seen.insert(ts[j]).second) ts[w++] = ts[j];
-            ts.resize(w);
-        }
-        off[r + 1] = static_cast<long long>(ts.size());
-    }
-    tvz_catalog *c = new tvz_catalog();
-    c->n_rows = n_rows;
-    c->n_vals = static_cast<long long>(ts.size());
-    c->n_pairs = (c->n_vals + 1) / 2;
-    c->n_pairs_padded = (c->n_pairs + kChunkPairs - 1) / kChunkPairs * kChunkPairs;
-    ts.resize(static_cast<size_t>(2 * c->n_pairs_padded), kPadPattern);
-    // coarse index: last row whose offset is <= b*1024 (clamped to the last row)
-    std::vector<int> block_row(static_cast<size_t>((2 * c->n_pairs_padded) >> kBlockShift) + 2, 0);
-    {
-        long long r = 0;
-        for (size_t b = 0; b < block_row.size(); ++b) {
-            const long long e = static_cast<long long>(b) << kBlockShift;
-            while (r + 1 < n_rows && off[r + 1] <= e) ++r;
-            block_row[b] = static_cast<int>(r);
-        }
-    }
-    // 16-bit fingerprints, padded to whole warp units (pad entries point past n_vals and are dropped)
-    c->n_units = (c->n_vals + kFpPerUnit - 1) / kFpPerUnit;
-    std::vector<unsigned short> fp(static_cast<size_t>(std::max<long long>(1, c->n_units)) * kFpPerUnit, 0);
-    std::vector<unsigned short> perm(fp.size(), 0);
-    arrange_fingerprints(ts.data(), c->n_vals, c->n_units, fp.data(), perm.data());
-    // verification records in ARRANGED order: a surviving fingerprint at position p is checked against
-    // rec[p].ts and, if it is a real match, adds into counts[rec[p].row] -- one 16-byte load, no search
-    // for the row.  Pad positions hold a NaN pattern that equals no query key.
-    std::vector<VerifyRec> rec(fp.size(), VerifyRec{kPadPattern, 0u, 0u});
-    {
-        std::vector<unsigned> row_of(kFpPerUnit);
-        long long r = 0;
-        for (long long u = 0; u < c->n_units; ++u) {
-            const long long base = u * kFpPerUnit;
-            for (int i = 0; i < kFpPerUnit && base + i < c->n_vals; ++i) {
-                while (r + 1 < n_rows && off[r + 1] <= base + i) ++r;
-                row_of[i] = static_cast<unsigned>(r);
-            }
-            for (int p2 = 0; p2 < kFpPerUnit; ++p2) {
-                const long long elem = base + perm[base + p2];
-                if (elem < c->n_vals) {
-                    rec[base + p2].ts = ts[elem];
-                    rec[base + p2].row = row_of[perm[base + p2]];
-                }
-            }
-        }
-    }
-    cudaGetDevice(&c->device);
-    auto fail = [&](cudaError_t e, const char *what) {
-        set_error(TVZ_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
-        tvz_catalog_destroy(c);
-        return TVZ_ERR_CUDA;
-    };
-    cudaError_t e;
-    if ((e = cudaMalloc(&c->d_ts, ts.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(ts)");
-    if ((e = cudaMalloc(&c->d_fp, fp.size() * 2)) != cudaSuccess) return fail(e, "cudaMalloc(fp)");
-    if ((e = cudaMemcpy(c->d_fp, fp.data(), fp.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess)
-        return fail(e, "cudaMemcpy(fp)");
-    if ((e = cudaMalloc(&c->d_rec, rec.size() * sizeof(VerifyRec))) != cudaSuccess) return fail(e, "cudaMalloc(rec)");
-    if ((e = cudaMemcpy(c->d_rec, rec.data(), rec.size() * sizeof(VerifyRec), cudaMemcpyHostToDevice)) != cudaSuccess)
-        return fail(e, "cudaMemcpy(rec)");
-    if ((e = cudaMalloc(&c->d_off, off.size() * 8)) != cudaSuccess) return fail(e, "cudaMalloc(off)");
-    if ((e = cudaMalloc(&c->d_vid, std::max<size_t>(1, n_rows) * 4)) != cudaSuccess) return fail(e, "cudaMalloc(vid)");
-    if ((e = cudaMalloc(&c->d_block_row, block_row.size() * 4)) != cudaSuccess) return fail(e, "cudaMalloc(block_row)");
-    if ((e = cudaMemcpy(c->d_block_row, block_row.data(), block_row.size() * 4, cudaMemcpyHostToDevice)) !=
-        cudaSuccess)
-        return fail(e, "cudaMemcpy(block_row)");
-    if ((e = cudaMemcpy(c->d_ts, ts.data(), ts.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
-        return fail(e, "cudaMemcpy(ts)");
-    if ((e = cudaMemcpy(c->d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
-        return fail(e, "cudaMemcpy(off)");
-    if (n_rows && (e = cudaMemcpy(c->d_vid, h_video_id, n_rows * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
-        return fail(e, "cudaMemcpy(vid)");
-    *out = c;
+template <int kQ, bool kParam>
+cudaError_t set_tile_attr() {
+    return cudaFuncSetAttribute(match_tile_kernel<kQ, kParam>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(TileSmem<kQ>)));
+}
+// Function attributes are set once per device, not per launch.
+int ensure_kernel_attrs() {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    TVZ_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return TVZ_OK;
+    TVZ_CUDA((set_tile_attr<1, true>()));
+    TVZ_CUDA((set_tile_attr<1, false>()));
+    TVZ_CUDA((set_tile_attr<kBatch, false>()));
+    if (dev >= 0 && dev < 64) done[dev] = true;
     return TVZ_OK;
-    });
 }
 
-void tvz_catalog_destroy(tvz_catalog *c) {
-    if (!c) return;
-    if (c->d_ts) cudaFree(c->d_ts);
-    if (c->d_fp) cudaFree(c->d_fp);
-    if (c->d_rec) cudaFree(c->d_rec);
-    if (c->d_off) cudaFree(c->d_off);
-    if (c->d_vid) cudaFree(c->d_vid);
-    if (c->d_block_row) cudaFree(c->d_block_row);
-    delete c;
-}
-
-int64_t tvz_catalog_rows(const tvz_catalog *c) { return c ? c->n_rows : 0; }
-int64_t tvz_catalog_values(const tvz_catalog *c) { return c ? c->n_vals : 0; }
-int64_t tvz_catalog_algo_bytes(const tvz_catalog *c) { return c ? 8 * c->n_vals + 8 * (c->n_rows + 1) : 0; }
-
-int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_ws **out) {
-    return guarded([&]() -> int {
-    TVZ_REQUIRE(cat && out, "null pointer");
-    *out = nullptr;
-    TVZ_REQUIRE(hit_capacity >= 0, "negative capacity");
-    tvz_match_ws *ws = new tvz_match_ws();
-    ws->cat = cat;
-    ws->cap = std::max<long long>(1, hit_capacity);
-    ws->n_blocks = static_cast<int>((cat->n_rows + kScanRowsPerBlock - 1) / kScanRowsPerBlock);
-    auto bail = [&](cudaError_t e, const char *what) {
-        set_error(TVZ_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
-        tvz_match_ws_destroy(ws);
-        return TVZ_ERR_CUDA;
-    };
-    cudaError_t e;
-    const size_t nr = std::max<long long>(1, cat->n_rows);
-    if ((e = cudaMalloc(&ws->d_counts, nr * 4)) != cudaSuccess) return bail(e, "cudaMalloc(counts)");
-    if ((e = cudaMemset(ws->d_counts, 0, nr * 4)) != cudaSuccess) return bail(e, "cudaMemset(counts)");
-    if ((e = cudaMalloc(&ws->d_state, std::max(1, ws->n_blocks) * 8)) != cudaSuccess) return bail(e, "cudaMalloc(state)");
-    if ((e = cudaMemset(ws->d_state, 0, std::max(1, ws->n_blocks) * 8)) != cudaSuccess) return bail(e, "cudaMemset(state)");
-    if ((e = cudaMalloc(&ws->d_ticket, 12)) != cudaSuccess) return bail(e, "cudaMalloc(ticket)");
-    {
-        const unsigned init[3] = {0u, 1u, 0u};
-        if ((e = cudaMemcpy(ws->d_ticket, init, 12, cudaMemcpyHostToDevice)) != cudaSuccess)
-            return bail(e, "cudaMemcpy(ticket)");
+// The catalogue as a query sees it: tail tile and mutation sequence, read under the lock.
+struct CatView {
+    TileDesc tail[kMaxTailTiles] = {};
+    int n_tiles = 0;
+    unsigned long long seq = 0;
+};
+CatView view_of(const tvz_catalog *cat) {
+    CatView v;
+    if (cat->tail_index >= 0) {
+        std::lock_guard<std::mutex> lk(cat->mu);
+        tail_descs(cat, v.tail);
+        v.n_tiles = static_cast<int>(cat->n_tiles());
+        v.seq = cat->mut_seq.load(std::memory_order_relaxed);
+    } else {
+        v.n_tiles = static_cast<int>(cat->tiles.size());
     }
-    if ((e = cudaMalloc(&ws->d_out, (ws->cap + 1) * 8)) != cudaSuccess) return bail(e, "cudaMalloc(out)");
-    if ((e = cudaMemset(ws->d_out, 0, 8)) != cudaSuccess) return bail(e, "cudaMemset(out)");
-    if ((e = cudaMalloc(&ws->d_rows, ws->cap * 8)) != cudaSuccess) return bail(e, "cudaMalloc(rows)");
-    if ((e = cudaMalloc(&ws->d_kth, ws->cap * 4)) != cudaSuccess) return bail(e, "cudaMalloc(kth)");
-    if ((e = cudaMalloc(&ws->d_nhits, 8)) != cudaSuccess) return bail(e, "cudaMalloc(nhits)");
-    if ((e = cudaMalloc(&ws->d_chunk_hits, (nr / kFusedChunk + 2) * 4)) != cudaSuccess)
-        return bail(e, "cudaMalloc(chunk_hits)");
-    if ((e = cudaMemset(ws->d_nhits, 0, 8)) != cudaSuccess) return bail(e, "cudaMemset(nhits)");
-    if ((e = cudaMalloc(&ws->d_keys, kMaxKeys * 8)) != cudaSuccess) return bail(e, "cudaMalloc(keys)");
-    if ((e = cudaMalloc(&ws->d_mult, kMaxKeys * 4)) != cudaSuccess) return bail(e, "cudaMalloc(mult)");
-    if ((e = cudaHostAlloc(&ws->h_out, (ws->cap + 1) * 8, cudaHostAllocDefault)) != cudaSuccess)
-        return bail(e, "cudaHostAlloc(out)");
-    if ((e = cudaHostAlloc(&ws->h_kth, ws->cap * 4, cudaHostAllocDefault)) != cudaSuccess)
-        return bail(e, "cudaHostAlloc(kth)");
-    if ((e = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking)) != cudaSuccess)
-        return bail(e, "cudaStreamCreate");
-    if ((e = cudaEventCreateWithFlags(&ws->staged, cudaEventDisableTiming)) != cudaSuccess)
-        return bail(e, "cudaEventCreate");
-    int rc = ensure_query_capacity(ws, 256);
-    if (rc) { tvz_match_ws_destroy(ws); return rc; }
-    // the memsets above ran on the legacy stream; queries run on non-blocking streams
-    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail(e, "cudaDeviceSynchronize");
-    *out = ws;
+    return v;
+}
+
+void base_args(const tvz_catalog *cat, tvz_match_ws *ws, const CatView &cv, TileArgs &a) {
+    a.fp = cat->d_fp;
+    a.rec = cat->d_rec;
+    a.tiles = cat->d_tiles;
+    memcpy(a.tail, cv.tail, sizeof(a.tail));
+    a.n_tiles = cv.n_tiles;
+    a.tail_index = cat->tail_index;
+    a.vid = cat->d_vid;
+    a.dead = cat->d_dead;
+    a.state = ws->d_state;
+    a.ctrl = ws->d_ctrl;
+    a.n_hits_out = ws->d_nhits;
+    a.trace = ws->d_trace;
+}
+
+// A query must see every upsert that returned before it was enqueued.
+int wait_for_mutations(const tvz_catalog *cat, tvz_match_ws *ws, const CatView &cv, cudaStream_t st) {
+    if (cat->tail_index >= 0 && cv.seq != 0 && (cv.seq != ws->seen_mut || st != ws->seen_stream)) {
+        TVZ_CUDA(cudaStreamWaitEvent(st, cat->mut_event, 0));
+        ws->seen_mut = cv.seq;
+        ws->seen_stream = st;
+    }
     return TVZ_OK;
-    });
 }
 
-void tvz_match_ws_destroy(tvz_match_ws *ws) {
-    if (!ws) return;
-    if (ws->stream) cudaStreamSynchronize(ws->stream);
-    if (ws->d_counts) cudaFree(ws->d_counts);
-    if (ws->d_state) cudaFree(ws->d_state);
-    if (ws->d_ticket) cudaFree(ws->d_ticket);
-    if (ws->d_out) cudaFree(ws->d_out);
-    if (ws->d_rows) cudaFree(ws->d_rows);
-    if (ws->d_kth) cudaFree(ws->d_kth);
-    if (ws->d_nhits) cudaFree(ws->d_nhits);
-    if (ws->d_chunk_hits) cudaFree(ws->d_chunk_hits);
-    if (ws->d_keys) cudaFree(ws->d_keys);
-    if (ws->d_mult) cudaFree(ws->d_mult);
-    if (ws->d_qcanon) cudaFree(ws->d_qcanon);
-    if (ws->h_stage) cudaFreeHost(ws->h_stage);
-    if (ws->h_out) cudaFreeHost(ws->h_out);
-    if (ws->h_kth) cudaFreeHost(ws->h_kth);
-    void *bdev[] = {ws->b_counts, ws->b_out, ws->b_mult, ws->b_nkeys, ws->b_rows, ws->b_nhits, ws->b_state, ws->b_keys,
-                    ws->b_ticket};
-    for (void *p : bdev)
-        if (p) cudaFree(p);
-    if (ws->hb_stage) cudaFreeHost(ws->hb_stage);
-    if (ws->hb_out) cudaFreeHost(ws->hb_out);
-    if (ws->staged) cudaEventDestroy(ws->staged);
-    if (ws->t0) cudaEventDestroy(ws->t0);
-    if (ws->t1) cudaEventDestroy(ws->t1);
-    if (ws->stream) cudaStreamDestroy(ws->stream);
-    delete ws;
-}
-
-const int32_t *tvz_match_ws_hits(const tvz_match_ws *ws) { return ws ? ws->d_out : nullptr; }
-const int64_t *tvz_match_ws_nhits(const tvz_match_ws *ws) {
-    return ws ? reinterpret_cast<const int64_t *>(ws->d_nhits) : nullptr;
-}
-const int32_t *tvz_match_ws_counts(const tvz_match_ws *ws) { return ws ? ws->d_counts : nullptr; }
-
-}  // extern "C"
-
-namespace {
-
-// Enqueue query upload + count + ordered compaction (+ kth) on `st`.  `want_kth` needs qn <= q_cap.
+// Enqueue query upload + the tile kernel (+ kth) on `st`.  `want_kth` needs qn <= q_cap.
 int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match, bool want_kth,
-                  int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr) {
+                  int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr,
+                  const unsigned *my_flags = nullptr) {
     TVZ_REQUIRE(cat && ws && ws->cat == cat, "workspace does not belong to this catalogue");
     TVZ_REQUIRE(qn >= 0 && (qn == 0 || h_q), "bad query");
     if (!d_out) {
@@ -1057,20 +891,22 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
     unsigned long long *h_qc = reinterpret_cast<unsigned long long *>(ws->h_stage);
     unsigned long long *h_keys = h_qc + ws->q_cap;
     int *h_mult = reinterpret_cast<int *>(h_keys + ws->q_cap);
-    std::vector<unsigned long long> sorted;
-    sorted.reserve(qn);
+    int n_sorted = 0;
+    bool ascending = true;   // by bit pattern, which is all the kernel's binary search needs
     for (int i = 0; i < qn; ++i) {
         const unsigned long long b = canon_bits(h_q[i]);
         h_qc[i] = b;
-        if (!is_nan_bits(b)) sorted.push_back(b);
+        if (is_nan_bits(b)) continue;
+        if (n_sorted && b < h_keys[n_sorted - 1]) ascending = false;
+        h_keys[n_sorted++] = b;
     }
-    std::sort(sorted.begin(), sorted.end());
+    if (!ascending) std::sort(h_keys, h_keys + n_sorted);   // production queries are ascending cut lists (app.py:231)
     int nk = 0;
-    for (size_t i = 0; i < sorted.size();) {
-        size_t j = i;
-        while (j < sorted.size() && sorted[j] == sorted[i]) ++j;
-        h_keys[nk] = sorted[i];
-        h_mult[nk] = static_cast<int>(j - i);
+    for (int i = 0; i < n_sorted;) {
+        int j = i;
+        while (j < n_sorted && h_keys[j] == h_keys[i]) ++j;
+        h_keys[nk] = h_keys[i];
+        h_mult[nk] = j - i;
         ++nk;
         i = j;
     }
@@ -1078,81 +914,51 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
     // common case (a short query riding in the kernel parameters) never is, so back-to-back
     // asynchronous queries pipeline on the stream without a host-side wait in between.
     bool staged_copy = false;
+    const CatView cv = view_of(cat);
+    rc = wait_for_mutations(cat, ws, cv, st);
+    if (rc) return rc;
     if (want_kth && qn > 0) {
         TVZ_CUDA(cudaMemcpyAsync(ws->d_qcanon, h_qc, sizeof(unsigned long long) * qn, cudaMemcpyHostToDevice, st));
         staged_copy = true;
     }
-    if (cat->n_rows > 0) {
-        const int sms = num_sms();
-        const long long want = (cat->n_units + kFpWarps - 1) / kFpWarps;   // at least one unit per warp
-        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(TVZ_FP_MINB) * sms)));
-        if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
-        // One launch for the whole query when the keys fit one count launch: the kernel compacts its own
-        // counts behind two grid-wide barriers (cooperative launch).  TVZ_NO_FUSE=1 keeps the two kernels.
-        static const bool fuse_ok = [] {
-            const char *e = getenv("TVZ_NO_FUSE");
-            return !(e && e[0] == '1');
-        }();
-        bool fused = fuse_ok && nk > 0 && nk <= kMaxKeys;
-        FusedCompact fc;
-        if (fused) {
-            fc.enabled = 1;
-            fc.min_match = min_match;
-            fc.n_rows = cat->n_rows;
-            fc.cap = out_cap;
-            fc.vid = cat->d_vid;
-            fc.out = d_out;
-            fc.rows_out = ws->d_rows;
-            fc.n_hits_out = ws->d_nhits;
-            fc.chunk_hits = ws->d_chunk_hits;
-            fc.done = ws->d_ticket + 2;
-            if (gather) fc.gt = *gather;
+    if (cv.n_tiles > 0) {
+        rc = ensure_kernel_attrs();
+        if (rc) return rc;
+        TileArgs a{};
+        base_args(cat, ws, cv, a);
+        a.n_queries = 1;
+        a.n_keys = nk;
+        a.min_match = min_match;
+        a.cap = out_cap;
+        a.out = d_out;
+        a.out_stride = 0;
+        a.rows_out = ws->d_rows;
+        if (gather) {
+            a.gt = *gather;
+            a.my_flags = my_flags;
         }
-        auto launch = [&](bool param, const unsigned long long *dk, const int *dm, int n, const SmallQuery &sq) -> int {
-            auto kern = param ? match_count_kernel<true> : match_count_kernel<false>;
-            TVZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(sizeof(FpSmem))));
-            cudaError_t le = launch_pdl(kern, dim3(fused ? 2 * sms : grid), dim3(kFpThreads), sizeof(FpSmem), st, fused,
-                                        cat->d_fp, cat->n_units, cat->d_rec, dk, dm, n, ws->d_counts, sq, fc);
-            if (le == cudaErrorCooperativeLaunchTooLarge && fused) {
-                // the device cannot hold 2 CTAs per SM right now (MPS limits, a debugger ...): two kernels
-                cudaGetLastError();
-                fused = false;
-                fc.enabled = 0;
-                le = launch_pdl(kern, dim3(grid), dim3(kFpThreads), sizeof(FpSmem), st, false, cat->d_fp, cat->n_units,
-                                cat->d_rec, dk, dm, n, ws->d_counts, sq, fc);
-            }
-            TVZ_CUDA(le);
-            return TVZ_OK;
-        };
-        if (nk <= kParamKeys) {
+        const bool param = nk <= kParamKeys;
+        if (!param) {
+            TVZ_CUDA(cudaMemcpyAsync(ws->d_keys, h_keys, sizeof(unsigned long long) * nk, cudaMemcpyHostToDevice, st));
+            TVZ_CUDA(cudaMemcpyAsync(ws->d_mult, h_mult, sizeof(int) * nk, cudaMemcpyHostToDevice, st));
+            a.keys_g = ws->d_keys;
+            a.mult_g = ws->d_mult;
+            staged_copy = true;
+        }
+        if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
+        const dim3 grid(static_cast<unsigned>(cv.n_tiles)), block(TileShape<1>::kThreads);
+        if (param) {
             SmallQuery sq;
             memcpy(sq.keys, h_keys, sizeof(unsigned long long) * nk);
             memcpy(sq.mult, h_mult, sizeof(int) * nk);
-            if (nk > 0) {
-                rc = launch(true, nullptr, nullptr, nk, sq);
-                if (rc) return rc;
-            }
+            TVZ_CUDA(launch_pdl(match_tile_kernel<1, true>, grid, block, sizeof(TileSmem<1>), st, a, cat->units, sq));
         } else {
-            for (int k0 = 0; k0 < nk; k0 += kMaxKeys) {
-                const int n = std::min(kMaxKeys, nk - k0);
-                TVZ_CUDA(cudaMemcpyAsync(ws->d_keys, h_keys + k0, sizeof(unsigned long long) * n,
-                                         cudaMemcpyHostToDevice, st));
-                TVZ_CUDA(cudaMemcpyAsync(ws->d_mult, h_mult + k0, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-                staged_copy = true;
-                rc = launch(false, ws->d_keys, ws->d_mult, n, SmallQuery{});
-                if (rc) return rc;
-            }
+            TVZ_CUDA(launch_pdl(match_tile_kernel<1, false>, grid, block, sizeof(TileSmem<1>), st, a, cat->units, SmallQuery{}));
         }
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
-        if (!fused) {
-            rc = compact_enqueue(ws->d_counts, cat->n_rows, min_match, cat->d_vid, d_out, ws->d_rows, out_cap,
-                                 ws->d_nhits, ws->d_state, ws->d_ticket, nullptr, nullptr, st, gather);
-            if (rc) return rc;
-        }
         if (want_kth) {
-            match_kth_kernel<<<2 * sms, 256, 0, st>>>(cat->d_ts, cat->d_off, ws->d_rows, d_out, out_cap,
-                                                      ws->d_qcanon, qn, min_match, ws->d_kth);
+            match_kth_kernel<<<2 * num_sms(), 256, 0, st>>>(cat->d_ts, cat->d_off, ws->d_rows, d_out, out_cap,
+                                                            ws->d_qcanon, qn, min_match, ws->d_kth);
             TVZ_CUDA(cudaGetLastError());
         }
     } else {
@@ -1167,11 +973,539 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
     return TVZ_OK;
 }
 
+int ensure_batch_buffers(tvz_match_ws *ws) {
+    if (ws->b_dev) return TVZ_OK;
+    TVZ_CUDA(cudaMalloc(&ws->b_out, kBatch * (ws->cap + 1) * 8));
+    TVZ_CUDA(cudaMalloc(&ws->b_dev, kBatchStageBytes));
+    TVZ_CUDA(cudaHostAlloc(&ws->hb_stage, kStageSlots * kBatchStageBytes, cudaHostAllocDefault));
+    TVZ_CUDA(cudaHostAlloc(&ws->hb_out, kBatch * (ws->cap + 1) * 8, cudaHostAllocDefault));
+    for (int i = 0; i < kStageSlots; ++i) TVZ_CUDA(cudaEventCreateWithFlags(&ws->b_staged[i], cudaEventDisableTiming));
+    return TVZ_OK;
+}
+
+// Up to kBatch queries in one pass: keys staged with ONE copy, one kernel; records land in
+// d_out [nb][out_stride] (NULL: the workspace's own b_out with out_stride = 2 * (cap + 1)).
+int enqueue_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all, const int64_t *q_off, int g0, int nb,
+                  int min_match, int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr,
+                  const unsigned *my_flags = nullptr) {
+    TVZ_REQUIRE(nb >= 1 && nb <= kBatch, "a batch holds 1..%d queries", kBatch);
+    int rc = ensure_batch_buffers(ws);
+    if (rc) return rc;
+    if (!d_out) {
+        d_out = ws->b_out;
+        if (out_cap <= 0) out_cap = ws->cap;
+    }
+    TVZ_REQUIRE(out_cap >= 1 && out_cap <= ws->cap, "output capacity %lld outside [1, %lld]", out_cap, ws->cap);
+    const int slot = ws->b_slot;
+    ws->b_slot = (slot + 1) % kStageSlots;
+    if (ws->b_stage_busy[slot]) { TVZ_CUDA(cudaEventSynchronize(ws->b_staged[slot])); ws->b_stage_busy[slot] = false; }
+    uint8_t *stage = ws->hb_stage + slot * kBatchStageBytes;
+    unsigned long long *h_keys = reinterpret_cast<unsigned long long *>(stage);
+    int *h_mult = reinterpret_cast<int *>(stage + kBatchKeysBytes);
+    int *h_nk = reinterpret_cast<int *>(stage + kBatchKeysBytes + kBatchMultBytes);
+    std::vector<unsigned long long> sorted;
+    for (int b = 0; b < kBatch; ++b) h_nk[b] = 0;
+    for (int b = 0; b < nb; ++b) {
+        const double *q = q_all + q_off[g0 + b];
+        const long long qn = q_off[g0 + b + 1] - q_off[g0 + b];
+        TVZ_REQUIRE(qn >= 0, "query offsets must be non-decreasing");
+        TVZ_REQUIRE(qn <= 65535, "query %d has %lld values: not batchable (16-bit counts)", g0 + b, qn);
+        sorted.clear();
+        for (long long i = 0; i < qn; ++i) {
+            const unsigned long long bits = canon_bits(q[i]);
+            if (!is_nan_bits(bits)) sorted.push_back(bits);
+        }
+        std::sort(sorted.begin(), sorted.end());
+        int nk = 0;
+        for (size_t i = 0; i < sorted.size();) {
+            size_t j = i;
+            while (j < sorted.size() && sorted[j] == sorted[i]) ++j;
+            TVZ_REQUIRE(nk < kParamKeys, "query %d has more than %d distinct values: not batchable", g0 + b, kParamKeys);
+            h_keys[b * kParamKeys + nk] = sorted[i];
+            h_mult[b * kParamKeys + nk] = static_cast<int>(j - i);
+            ++nk;
+            i = j;
+        }
+        h_nk[b] = nk;
+    }
+    const CatView cv = view_of(cat);
+    rc = wait_for_mutations(cat, ws, cv, st);
+    if (rc) return rc;
+    if (cv.n_tiles == 0) {
+        TVZ_REQUIRE(!gather || gather->n_peers == 0, "an empty shard cannot take part in the fused gather");
+        for (int b = 0; b < nb; ++b) TVZ_CUDA(cudaMemsetAsync(d_out + b * 2 * (out_cap + 1), 0, 8, st));
+        TVZ_CUDA(cudaMemsetAsync(ws->d_nhits, 0, 8 * kBatch, st));
+        return TVZ_OK;
+    }
+    rc = ensure_kernel_attrs();
+    if (rc) return rc;
+    TVZ_CUDA(cudaMemcpyAsync(ws->b_dev, stage, kBatchStageBytes, cudaMemcpyHostToDevice, st));
+    TVZ_CUDA(cudaEventRecord(ws->b_staged[slot], st));
+    ws->b_stage_busy[slot] = true;
+    TileArgs a{};
+    base_args(cat, ws, cv, a);
+    a.keys_g = reinterpret_cast<const unsigned long long *>(ws->b_dev);
+    a.mult_g = reinterpret_cast<const int *>(ws->b_dev + kBatchKeysBytes);
+    a.n_keys_g = reinterpret_cast<const int *>(ws->b_dev + kBatchKeysBytes + kBatchMultBytes);
+    a.key_stride = kParamKeys;
+    a.n_queries = nb;
+    a.min_match = min_match;
+    a.cap = out_cap;
+    a.out = d_out;
+    a.out_stride = 2 * (out_cap + 1);
+    a.rows_out = nullptr;
+    if (gather) {
+        a.gt = *gather;
+        a.gt.query_stride = a.out_stride;
+        a.my_flags = my_flags;
+    }
+    if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
+    TVZ_CUDA(launch_pdl(match_tile_kernel<kBatch, false>, dim3(static_cast<unsigned>(cv.n_tiles)),
+                        dim3(TileShape<kBatch>::kThreads), sizeof(TileSmem<kBatch>), st, a, cat->units, SmallQuery{}));
+    if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
+    return TVZ_OK;
+}
+
+int make_gather(int n_peers, const uint64_t *peer_record, const uint64_t *peer_flag, const uint32_t *d_my_flags,
+                uint32_t epoch, GatherTargets &gt) {
+    TVZ_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers, "n_peers %d outside [1, %d]", n_peers, kMaxPeers);
+    TVZ_REQUIRE(peer_record && peer_flag && d_my_flags, "null pointer");
+    gt.n_peers = n_peers;
+    gt.epoch = epoch;
+    for (int p = 0; p < n_peers; ++p) {
+        gt.record[p] = reinterpret_cast<int *>(static_cast<uintptr_t>(peer_record[p]));
+        gt.flag[p] = reinterpret_cast<unsigned *>(static_cast<uintptr_t>(peer_flag[p]));
+    }
+    return TVZ_OK;
+}
+
+void free_catalog_device(tvz_catalog *c) {
+    void *dev[] = {c->d_fp, c->d_rec, c->d_ts, c->d_off, c->d_vid, c->d_dead, c->d_tiles, c->d_stage};
+    for (void *p : dev)
+        if (p) cudaFree(p);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->mut_event) cudaEventDestroy(c->mut_event);
+    if (c->mut_stream) cudaStreamDestroy(c->mut_stream);
+}
+
+int catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_video_id, int64_t n_rows,
+                   int64_t tail_values, tvz_catalog **out) {
+    TVZ_REQUIRE(out, "null out pointer");
+    *out = nullptr;
+    TVZ_REQUIRE(n_rows >= 0 && tail_values >= 0, "negative size");
+    TVZ_REQUIRE(n_rows < (1ll << 31) - kTailRows, "too many rows for one shard");
+    TVZ_REQUIRE(n_rows == 0 || (h_off && h_video_id), "null offsets/video ids");
+    TVZ_REQUIRE(n_rows == 0 || h_off[0] == 0, "offsets must start at 0");
+    for (int64_t r = 0; r < n_rows; ++r)
+        TVZ_REQUIRE(h_off[r + 1] >= h_off[r], "offsets must be non-decreasing (row %lld)", (long long)r);
+    const int64_t n_in = n_rows ? h_off[n_rows] : 0;
+    TVZ_REQUIRE(n_in == 0 || h_ts, "null timestamps");
+
+    // canonicalise: drop NaN, fold -0.0, drop in-row repeats (first occurrence kept)
+    std::vector<unsigned long long> ts;
+    ts.reserve(static_cast<size_t>(n_in) + 2);
+    std::vector<long long> off(static_cast<size_t>(n_rows) + 1, 0);
+    std::unordered_set<unsigned long long> seen;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        canon_row(h_ts + h_off[r], h_off[r + 1] - h_off[r], ts, seen);
+        off[r + 1] = static_cast<long long>(ts.size());
+    }
+    TVZ_REQUIRE(static_cast<long long>(ts.size() / kFpPerUnit) + tail_values / kFpPerUnit + 4 < (1ll << 22),
+                "too many stored values for one shard");
+    tvz_catalog *c = new tvz_catalog();
+    c->n_rows_main = n_rows;
+    c->n_vals_main = static_cast<long long>(ts.size());
+    c->n_units_main = (c->n_vals_main + kFpPerUnit - 1) / kFpPerUnit;
+    c->ts_main_padded = c->n_units_main * kFpPerUnit;
+    const bool is_mutable = tail_values > 0;
+    c->tail_cap_vals = is_mutable ? (tail_values + kFpPerUnit - 1) / kFpPerUnit * kFpPerUnit : 0;
+    const long long n_units_all = c->n_units_main + c->tail_cap_vals / kFpPerUnit;
+    const long long rows_cap = n_rows + (is_mutable ? kTailRows : 0);
+
+    // one wave of CTAs (2 per SM), one of them kept for the tail tile
+    const int want = std::max(1, 2 * num_sms() - (is_mutable ? 1 : 0));
+    build_tiles(off, n_rows, want, c->tiles);
+    if (is_mutable) {
+        c->tail_index = static_cast<int>(c->tiles.size());
+        c->h_off = off;
+    }
+    fill_units(c);
+
+    // 16-bit fingerprints, padded to whole warp units (pad entries point past n_vals and are dropped)
+    const size_t n_pos_main = static_cast<size_t>(std::max<long long>(1, c->n_units_main)) * kFpPerUnit;
+    std::vector<unsigned short> fp(n_pos_main, 0);
+    std::vector<unsigned short> perm(n_pos_main, 0);
+    arrange_fingerprints(ts.data(), c->n_vals_main, c->n_units_main, fp.data(), perm.data());
+    // verification records in ARRANGED order: a surviving fingerprint at position p is checked against
+    // rec[p].ts and, if it is a real match, adds into the count of rec[p].row -- one 16-byte load, no search
+    // for the row.  Pad positions hold a NaN pattern that equals no query key.
+    std::vector<VerifyRec> rec(n_pos_main, VerifyRec{kPadPattern, 0u, 0u});
+    {
+        std::vector<unsigned> row_of(kFpPerUnit);
+        long long r = 0;
+        for (long long u = 0; u < c->n_units_main; ++u) {
+            const long long base = u * kFpPerUnit;
+            for (int i = 0; i < kFpPerUnit && base + i < c->n_vals_main; ++i) {
+                while (r + 1 < n_rows && off[r + 1] <= base + i) ++r;
+                row_of[i] = static_cast<unsigned>(r);
+            }
+            for (int p2 = 0; p2 < kFpPerUnit; ++p2) {
+                const long long elem = base + perm[base + p2];
+                if (elem < c->n_vals_main) {
+                    rec[base + p2].ts = ts[elem];
+                    rec[base + p2].row = row_of[perm[base + p2]];
+                }
+            }
+        }
+    }
+    ts.resize(static_cast<size_t>(c->ts_main_padded), kPadPattern);
+
+    cudaGetDevice(&c->device);
+    auto fail = [&](cudaError_t e, const char *what) {
+        set_error(TVZ_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        tvz_catalog_destroy(c);
+        return TVZ_ERR_CUDA;
+    };
+    cudaError_t e;
+    const size_t n_pos_all = static_cast<size_t>(std::max<long long>(1, n_units_all)) * kFpPerUnit;
+    const size_t n_ts_all = static_cast<size_t>(std::max<long long>(1, c->ts_main_padded + c->tail_cap_vals));
+    if ((e = cudaMalloc(&c->d_fp, n_pos_all * 2)) != cudaSuccess) return fail(e, "cudaMalloc(fp)");
+    if ((e = cudaMalloc(&c->d_rec, n_pos_all * sizeof(VerifyRec))) != cudaSuccess) return fail(e, "cudaMalloc(rec)");
+    if ((e = cudaMalloc(&c->d_ts, n_ts_all * 8)) != cudaSuccess) return fail(e, "cudaMalloc(ts)");
+    if ((e = cudaMalloc(&c->d_off, (rows_cap + 1) * 8)) != cudaSuccess) return fail(e, "cudaMalloc(off)");
+    if ((e = cudaMalloc(&c->d_vid, std::max<size_t>(1, rows_cap) * 4)) != cudaSuccess) return fail(e, "cudaMalloc(vid)");
+    if ((e = cudaMalloc(&c->d_dead, std::max<size_t>(1, rows_cap))) != cudaSuccess) return fail(e, "cudaMalloc(dead)");
+    if ((e = cudaMalloc(&c->d_tiles, std::max<size_t>(1, c->tiles.size()) * sizeof(TileDesc))) != cudaSuccess)
+        return fail(e, "cudaMalloc(tiles)");
+    if ((e = cudaMemset(c->d_dead, 0, std::max<size_t>(1, rows_cap))) != cudaSuccess) return fail(e, "cudaMemset(dead)");
+    if ((e = cudaMemcpy(c->d_fp, fp.data(), fp.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(fp)");
+    if ((e = cudaMemcpy(c->d_rec, rec.data(), rec.size() * sizeof(VerifyRec), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(rec)");
+    if (!ts.empty() && (e = cudaMemcpy(c->d_ts, ts.data(), ts.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(ts)");
+    if ((e = cudaMemcpy(c->d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(off)");
+    if (n_rows && (e = cudaMemcpy(c->d_vid, h_video_id, n_rows * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(vid)");
+    if (!c->tiles.empty() &&
+        (e = cudaMemcpy(c->d_tiles, c->tiles.data(), c->tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(tiles)");
+    if (is_mutable) {
+        // the tail starts as padding: fingerprint 0 may pass a filter, the NaN record behind it never verifies
+        std::vector<VerifyRec> pad(static_cast<size_t>(c->tail_cap_vals), VerifyRec{kPadPattern, 0u, 0u});
+        if ((e = cudaMemset(c->d_fp + c->n_units_main * kFpPerUnit, 0, c->tail_cap_vals * 2)) != cudaSuccess)
+            return fail(e, "cudaMemset(tail fp)");
+        if ((e = cudaMemcpy(c->d_rec + c->n_units_main * kFpPerUnit, pad.data(), pad.size() * sizeof(VerifyRec),
+                            cudaMemcpyHostToDevice)) != cudaSuccess)
+            return fail(e, "cudaMemcpy(tail rec)");
+        if ((e = cudaStreamCreateWithFlags(&c->mut_stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return fail(e, "cudaStreamCreate");
+        if ((e = cudaEventCreateWithFlags(&c->mut_event, cudaEventDisableTiming)) != cudaSuccess)
+            return fail(e, "cudaEventCreate");
+        c->tail_vals.reserve(static_cast<size_t>(c->tail_cap_vals));
+        // video ids of the packed rows are needed to find the row an upsert replaces
+        c->row_of_vid.clear();
+        c->row_map_built = false;
+    }
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(e, "cudaDeviceSynchronize");
+    *out = c;
+    return TVZ_OK;
+}
+
+// Rebuild the tail from its live rows (host mirror) when it has filled up with replaced rows.
+// Called with the lock held and no query in flight (the caller's contract for upserts).
+int compact_tail(tvz_catalog *c) {
+    std::vector<TailRow> rows;
+    std::vector<unsigned long long> vals;
+    for (const TailRow &r : c->tail_rows) {
+        if (!r.alive) continue;
+        TailRow n = r;
+        n.start = static_cast<long long>(vals.size());
+        vals.insert(vals.end(), c->tail_vals.begin() + r.start, c->tail_vals.begin() + r.start + r.n);
+        rows.push_back(n);
+    }
+    const long long nv = static_cast<long long>(vals.size());
+    const size_t cap = static_cast<size_t>(c->tail_cap_vals);
+    std::vector<unsigned short> fp(cap, 0);
+    std::vector<VerifyRec> rec(cap, VerifyRec{kPadPattern, 0u, 0u});
+    std::vector<unsigned long long> ts(cap, kPadPattern);
+    std::vector<long long> off(kTailRows + 1, c->ts_main_padded);
+    std::vector<int> vid(kTailRows, 0);
+    std::vector<unsigned char> dead(kTailRows, 0);
+    for (size_t k = 0; k < rows.size(); ++k) {
+        const long long row = c->n_rows_main + static_cast<long long>(k);
+        for (int i = 0; i < rows[k].n; ++i) {
+            const unsigned long long v = vals[rows[k].start + i];
+            fp[rows[k].start + i] = static_cast<unsigned short>(filter_hash(v));
+            rec[rows[k].start + i] = VerifyRec{v, static_cast<unsigned>(row), 0u};
+            ts[rows[k].start + i] = v;
+        }
+        off[k] = c->ts_main_padded + rows[k].start;
+        off[k + 1] = c->ts_main_padded + rows[k].start + rows[k].n;
+        vid[k] = rows[k].vid;
+        c->row_of_vid[rows[k].vid] = row;
+    }
+    cudaStream_t st = c->mut_stream;
+    const long long p0 = c->n_units_main * kFpPerUnit;
+    TVZ_CUDA(cudaMemcpyAsync(c->d_fp + p0, fp.data(), cap * 2, cudaMemcpyHostToDevice, st));
+    TVZ_CUDA(cudaMemcpyAsync(c->d_rec + p0, rec.data(), cap * sizeof(VerifyRec), cudaMemcpyHostToDevice, st));
+    TVZ_CUDA(cudaMemcpyAsync(c->d_ts + c->ts_main_padded, ts.data(), cap * 8, cudaMemcpyHostToDevice, st));
+    TVZ_CUDA(cudaMemcpyAsync(c->d_off + c->n_rows_main, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+    TVZ_CUDA(cudaMemcpyAsync(c->d_vid + c->n_rows_main, vid.data(), vid.size() * 4, cudaMemcpyHostToDevice, st));
+    TVZ_CUDA(cudaMemcpyAsync(c->d_dead + c->n_rows_main, dead.data(), dead.size(), cudaMemcpyHostToDevice, st));
+    TVZ_CUDA(cudaStreamSynchronize(st));   // the host vectors go out of scope
+    c->tail_rows.swap(rows);
+    c->tail_vals.swap(vals);
+    c->tail_used_vals = nv;
+    c->tail_used_rows = static_cast<int>(c->tail_rows.size());
+    return TVZ_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
-// Debug hooks (not in the public header): time the count kernel of the last query with CUDA
+int tvz_catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_video_id, int64_t n_rows,
+                       tvz_catalog **out) {
+    return guarded([&]() -> int { return catalog_create(h_ts, h_off, h_video_id, n_rows, 0, out); });
+}
+
+int tvz_catalog_create_mutable(const double *h_ts, const int64_t *h_off, const int32_t *h_video_id, int64_t n_rows,
+                               int64_t tail_values, tvz_catalog **out) {
+    return guarded([&]() -> int {
+        TVZ_REQUIRE(tail_values >= 1, "a mutable catalogue needs room for appended values");
+        return catalog_create(h_ts, h_off, h_video_id, n_rows, tail_values, out);
+    });
+}
+
+void tvz_catalog_destroy(tvz_catalog *c) {
+    if (!c) return;
+    if (c->mut_stream) cudaStreamSynchronize(c->mut_stream);
+    free_catalog_device(c);
+    delete c;
+}
+
+int64_t tvz_catalog_rows(const tvz_catalog *c) {
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return c->n_rows();
+}
+int64_t tvz_catalog_values(const tvz_catalog *c) {
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return c->n_vals_main + c->tail_used_vals;
+}
+int64_t tvz_catalog_algo_bytes(const tvz_catalog *c) {
+    return c ? 8 * tvz_catalog_values(c) + 8 * (tvz_catalog_rows(c) + 1) : 0;
+}
+int tvz_catalog_tiles(const tvz_catalog *c) {
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return static_cast<int>(c->n_tiles());
+}
+
+/* Row upsert (db.py:43-64): the first live row of `video_id` is replaced, or a new row is appended.
+ * Contract: no query on this catalogue is in flight while an upsert runs (the Python Inspector holds a
+ * reader/writer lock); queries enqueued afterwards see it.  TVZ_ERR_OVERFLOW: the tail is full even
+ * after dropping replaced rows -- repack the catalogue. */
+int tvz_catalog_upsert(tvz_catalog *c, int32_t video_id, const double *h_ts, int n) {
+    return guarded([&]() -> int {
+    TVZ_REQUIRE(c && n >= 0 && (n == 0 || h_ts), "bad arguments");
+    TVZ_REQUIRE(c->tail_index >= 0, "this catalogue was created immutable (tvz_catalog_create_mutable)");
+    std::vector<unsigned long long> vals;
+    std::unordered_set<unsigned long long> seen;
+    canon_row(h_ts, n, vals, seen);
+    const int nv = static_cast<int>(vals.size());
+    std::lock_guard<std::mutex> lk(c->mu);
+    TVZ_REQUIRE(nv <= c->tail_cap_vals, "a row of %d values does not fit the tail (%lld)", nv, c->tail_cap_vals);
+    if (!c->row_map_built) {   // first upsert: index the packed rows by video id (first row wins, db.py:47)
+        std::vector<int> vid(static_cast<size_t>(c->n_rows_main));
+        if (c->n_rows_main) TVZ_CUDA(cudaMemcpy(vid.data(), c->d_vid, vid.size() * 4, cudaMemcpyDeviceToHost));
+        c->row_of_vid.reserve(vid.size() * 2);
+        for (long long r = 0; r < c->n_rows_main; ++r) c->row_of_vid.emplace(vid[r], r);
+        c->row_map_built = true;
+    }
+    UpsertArgs u{};
+    u.kill_row = -1;
+    long long old_row = -1;
+    auto it = c->row_of_vid.find(video_id);
+    if (it != c->row_of_vid.end()) old_row = it->second;
+    const bool old_is_last_tail = old_row >= c->n_rows_main && old_row == c->n_rows() - 1;
+    // room: a replaced last tail row is rewritten in place, everything else is appended
+    long long start = old_is_last_tail ? c->tail_rows.back().start : c->tail_used_vals;
+    if (start + nv > c->tail_cap_vals || (!old_is_last_tail && c->tail_used_rows >= kTailRows)) {
+        if (old_row >= c->n_rows_main) {   // it is being replaced anyway: do not carry it over
+            c->tail_rows[old_row - c->n_rows_main].alive = false;
+            c->row_of_vid.erase(video_id);
+            old_row = -1;
+        }
+        int rc = compact_tail(c);
+        if (rc) return rc;
+        if (c->tail_used_vals + nv > c->tail_cap_vals || c->tail_used_rows >= kTailRows)
+            return set_error(TVZ_ERR_OVERFLOW, "catalogue tail is full (%d live rows, %lld values): repack",
+                             c->tail_used_rows, c->tail_used_vals);
+        start = c->tail_used_vals;
+        it = c->row_of_vid.find(video_id);
+        old_row = it != c->row_of_vid.end() ? it->second : -1;
+    }
+    const bool in_place = old_row >= c->n_rows_main && old_row == c->n_rows() - 1;
+    if (old_row >= 0) {
+        u.kill_row = old_row;
+        if (old_row < c->n_rows_main) {
+            const long long a = c->h_off[old_row], b = c->h_off[old_row + 1];
+            u.kill_pos_lo = a / kFpPerUnit * kFpPerUnit;
+            u.kill_pos_hi = b > a ? (b + kFpPerUnit - 1) / kFpPerUnit * kFpPerUnit : u.kill_pos_lo;
+            u.kill_ts_lo = a;
+            u.kill_ts_hi = b;
+            ++c->dead_main;
+        } else {
+            TailRow &tr = c->tail_rows[old_row - c->n_rows_main];
+            u.kill_pos_lo = c->n_units_main * kFpPerUnit + tr.start;
+            u.kill_pos_hi = u.kill_pos_lo + tr.n;
+            u.kill_ts_lo = c->ts_main_padded + tr.start;
+            u.kill_ts_hi = u.kill_ts_lo + tr.n;
+            tr.alive = false;
+        }
+    }
+    long long new_row;
+    if (in_place) {
+        new_row = old_row;
+        TailRow &tr = c->tail_rows.back();
+        tr.n = nv;
+        tr.alive = true;
+        c->tail_vals.resize(static_cast<size_t>(tr.start));
+    } else {
+        new_row = c->n_rows();
+        c->tail_rows.push_back(TailRow{video_id, start, nv, true});
+        ++c->tail_used_rows;
+    }
+    c->tail_vals.insert(c->tail_vals.end(), vals.begin(), vals.end());
+    c->tail_used_vals = start + nv;
+    c->row_of_vid[video_id] = new_row;
+    u.rec = c->d_rec;
+    u.fp = c->d_fp;
+    u.ts = c->d_ts;
+    u.off = c->d_off;
+    u.vid = c->d_vid;
+    u.dead = c->d_dead;
+    u.new_row = new_row;
+    u.pos0 = c->n_units_main * kFpPerUnit + start;
+    u.ts0 = c->ts_main_padded + start;
+    u.new_vid = video_id;
+    u.n = nv;
+    if (nv <= kParamKeys) {
+        memcpy(u.vals, vals.data(), sizeof(unsigned long long) * nv);
+    } else {
+        if (nv > c->stage_cap) {
+            TVZ_CUDA(cudaStreamSynchronize(c->mut_stream));
+            if (c->d_stage) cudaFree(c->d_stage);
+            if (c->h_stage) cudaFreeHost(c->h_stage);
+            c->d_stage = nullptr;
+            c->h_stage = nullptr;
+            c->stage_cap = 0;
+            long long cap = 1024;
+            while (cap < nv) cap *= 2;
+            TVZ_CUDA(cudaMalloc(&c->d_stage, cap * 8));
+            TVZ_CUDA(cudaHostAlloc(&c->h_stage, cap * 8, cudaHostAllocDefault));
+            c->stage_cap = cap;
+        }
+        TVZ_CUDA(cudaStreamSynchronize(c->mut_stream));   // the previous long row has left the staging buffer
+        memcpy(c->h_stage, vals.data(), sizeof(unsigned long long) * nv);
+        TVZ_CUDA(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof(unsigned long long) * nv, cudaMemcpyHostToDevice, c->mut_stream));
+        u.vals_g = c->d_stage;
+    }
+    upsert_kernel<<<1, 512, 0, c->mut_stream>>>(u);
+    TVZ_CUDA(cudaGetLastError());
+    TVZ_CUDA(cudaEventRecord(c->mut_event, c->mut_stream));
+    c->mut_seq.fetch_add(1, std::memory_order_relaxed);
+    return TVZ_OK;
+    });
+}
+
+/* {rows in the tail, values in the tail, value capacity, replaced rows of the packed part} */
+int tvz_catalog_tail_info(const tvz_catalog *c, int64_t *out4) {
+    TVZ_REQUIRE(c && out4, "null pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    out4[0] = c->tail_used_rows;
+    out4[1] = c->tail_used_vals;
+    out4[2] = c->tail_cap_vals;
+    out4[3] = c->dead_main;
+    return TVZ_OK;
+}
+
+int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_ws **out) {
+    return guarded([&]() -> int {
+    TVZ_REQUIRE(cat && out, "null pointer");
+    *out = nullptr;
+    TVZ_REQUIRE(hit_capacity >= 0, "negative capacity");
+    tvz_match_ws *ws = new tvz_match_ws();
+    ws->cat = cat;
+    ws->cap = std::max<long long>(1, hit_capacity);
+    auto bail = [&](cudaError_t e, const char *what) {
+        set_error(TVZ_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        tvz_match_ws_destroy(ws);
+        return TVZ_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
+    cudaStream_t st = ws->stream;
+    const size_t n_state = static_cast<size_t>(std::max<long long>(1, cat->max_tiles())) * kBatch;
+    if ((e = cudaMalloc(&ws->d_state, n_state * 8)) != cudaSuccess) return bail(e, "cudaMalloc(state)");
+    if ((e = cudaMemsetAsync(ws->d_state, 0, n_state * 8, st)) != cudaSuccess) return bail(e, "cudaMemset(state)");
+    if ((e = cudaMalloc(&ws->d_ctrl, 8)) != cudaSuccess) return bail(e, "cudaMalloc(ctrl)");
+    if ((e = cudaMalloc(&ws->d_out, (ws->cap + 1) * 8)) != cudaSuccess) return bail(e, "cudaMalloc(out)");
+    if ((e = cudaMemsetAsync(ws->d_out, 0, 8, st)) != cudaSuccess) return bail(e, "cudaMemset(out)");
+    if ((e = cudaMalloc(&ws->d_rows, ws->cap * 8)) != cudaSuccess) return bail(e, "cudaMalloc(rows)");
+    if ((e = cudaMalloc(&ws->d_kth, ws->cap * 4)) != cudaSuccess) return bail(e, "cudaMalloc(kth)");
+    if ((e = cudaMalloc(&ws->d_nhits, 8 * kBatch)) != cudaSuccess) return bail(e, "cudaMalloc(nhits)");
+    if ((e = cudaMemsetAsync(ws->d_nhits, 0, 8 * kBatch, st)) != cudaSuccess) return bail(e, "cudaMemset(nhits)");
+    if ((e = cudaHostAlloc(&ws->h_out, (ws->cap + 1) * 8, cudaHostAllocDefault)) != cudaSuccess)
+        return bail(e, "cudaHostAlloc(out)");
+    if ((e = cudaHostAlloc(&ws->h_kth, ws->cap * 4, cudaHostAllocDefault)) != cudaSuccess)
+        return bail(e, "cudaHostAlloc(kth)");
+    if ((e = cudaEventCreateWithFlags(&ws->staged, cudaEventDisableTiming)) != cudaSuccess)
+        return bail(e, "cudaEventCreate");
+    int rc = ensure_query_capacity(ws, 256);
+    if (rc) { tvz_match_ws_destroy(ws); return rc; }
+    // {query epoch = 1, finished CTAs = 0} through the pinned staging buffer, on the workspace's own stream
+    reinterpret_cast<unsigned *>(ws->h_stage)[0] = 1u;
+    reinterpret_cast<unsigned *>(ws->h_stage)[1] = 0u;
+    if ((e = cudaMemcpyAsync(ws->d_ctrl, ws->h_stage, 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return bail(e, "cudaMemcpy(ctrl)");
+    // queries may run on other streams: the initialisation must have landed before the first one
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");
+    *out = ws;
+    return TVZ_OK;
+    });
+}
+
+void tvz_match_ws_destroy(tvz_match_ws *ws) {
+    if (!ws) return;
+    if (ws->stream) cudaStreamSynchronize(ws->stream);
+    void *dev[] = {ws->d_state, ws->d_ctrl, ws->d_out, ws->d_rows, ws->d_kth, ws->d_nhits, ws->d_qcanon, ws->d_mult,
+                   ws->b_out, ws->b_dev};
+    for (void *p : dev)
+        if (p) cudaFree(p);
+    void *host[] = {ws->h_stage, ws->h_out, ws->h_kth, ws->hb_stage, ws->hb_out};
+    for (void *p : host)
+        if (p) cudaFreeHost(p);
+    if (ws->staged) cudaEventDestroy(ws->staged);
+    for (cudaEvent_t e : ws->b_staged)
+        if (e) cudaEventDestroy(e);
+    if (ws->t0) cudaEventDestroy(ws->t0);
+    if (ws->t1) cudaEventDestroy(ws->t1);
+    if (ws->stream) cudaStreamDestroy(ws->stream);
+    delete ws;
+}
+
+const int32_t *tvz_match_ws_hits(const tvz_match_ws *ws) { return ws ? ws->d_out : nullptr; }
+const int64_t *tvz_match_ws_nhits(const tvz_match_ws *ws) {
+    return ws ? reinterpret_cast<const int64_t *>(ws->d_nhits) : nullptr;
+}
+
+// Debug hooks (not in the public header): time the kernel of the last query with CUDA
 // events recorded on the query's own stream.
 int tvz_debug_match_timing(tvz_match_ws *ws, int enable) {
     TVZ_REQUIRE(ws, "null workspace");
@@ -1180,6 +1514,11 @@ int tvz_debug_match_timing(tvz_match_ws *ws, int enable) {
         TVZ_CUDA(cudaEventCreate(&ws->t1));
     }
     ws->timing = enable != 0;
+    return TVZ_OK;
+}
+int tvz_debug_tile_trace(tvz_match_ws *ws, long long *d_trace) {   // int64 [tiles][8] on the device, or NULL to stop
+    TVZ_REQUIRE(ws, "null workspace");
+    ws->d_trace = d_trace;
     return TVZ_OK;
 }
 int tvz_debug_match_count_ms(tvz_match_ws *ws, float *ms) {
@@ -1201,6 +1540,21 @@ int tvz_debug_arrange_fingerprints(const double *values, int64_t n, uint16_t *fp
     });
 }
 
+// Debug hook (host only): the tiling of a catalogue with the given CSR offsets for `want` tiles.
+// tiles_out: int32 [max_tiles][4] = {row_lo, n_rows, unit_lo, unit_hi}; returns the number of tiles.
+int tvz_debug_build_tiles(const int64_t *off, int64_t n_rows, int want, int32_t *tiles_out, int max_tiles) {
+    std::vector<long long> o(off, off + n_rows + 1);
+    std::vector<TileDesc> t;
+    build_tiles(o, n_rows, std::max(1, want), t);
+    for (size_t i = 0; i < t.size() && static_cast<int>(i) < max_tiles; ++i) {
+        tiles_out[4 * i] = t[i].row_lo;
+        tiles_out[4 * i + 1] = t[i].n_rows;
+        tiles_out[4 * i + 2] = static_cast<int>(t[i].unit_lo);
+        tiles_out[4 * i + 3] = static_cast<int>(t[i].unit_hi);
+    }
+    return static_cast<int>(t.size());
+}
+
 int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match,
                             int32_t *d_out, int64_t out_cap, void *stream) {
     return guarded([&]() -> int {
@@ -1212,20 +1566,12 @@ int tvz_catalog_match_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, con
                                    int min_match, int n_peers, const uint64_t *peer_record, const uint64_t *peer_flag,
                                    const uint32_t *d_my_flags, int64_t out_cap, uint32_t epoch, void *stream) {
     return guarded([&]() -> int {
-    TVZ_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers, "n_peers %d outside [1, %d]", n_peers, kMaxPeers);
-    TVZ_REQUIRE(peer_record && peer_flag && d_my_flags, "null pointer");
-    TVZ_REQUIRE(cat && cat->n_rows > 0, "the fused gather needs a non-empty shard");
+    TVZ_REQUIRE(cat && cat->max_tiles() > 0, "the fused gather needs a non-empty shard");
     GatherTargets gt;
-    gt.n_peers = n_peers;
-    gt.epoch = epoch;
-    for (int p = 0; p < n_peers; ++p) {
-        gt.record[p] = reinterpret_cast<int *>(static_cast<uintptr_t>(peer_record[p]));
-        gt.flag[p] = reinterpret_cast<unsigned *>(static_cast<uintptr_t>(peer_flag[p]));
-    }
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = enqueue_match(cat, ws, h_q, qn, min_match, false, nullptr, out_cap, st, &gt);
+    int rc = make_gather(n_peers, peer_record, peer_flag, d_my_flags, epoch, gt);
     if (rc) return rc;
-    return gather_wait_enqueue(d_my_flags, n_peers, epoch, st);
+    return enqueue_match(cat, ws, h_q, qn, min_match, false, nullptr, out_cap, static_cast<cudaStream_t>(stream), &gt,
+                         d_my_flags);
     });
 }
 
@@ -1269,44 +1615,52 @@ int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q,
     });
 }
 
-}  // extern "C"
-
-namespace {
-
-int ensure_batch_buffers(tvz_match_ws *ws) {
-    const tvz_catalog *cat = ws->cat;
-    if (ws->b_counts && ws->hb_cap == ws->cap) return TVZ_OK;
-    TVZ_REQUIRE(!ws->b_counts, "batch buffers cannot be resized");  // cap is fixed per workspace
-    const size_t nr = std::max<long long>(1, cat->n_rows);
-    const size_t nb = std::max(1, ws->n_blocks);
-    TVZ_CUDA(cudaMalloc(&ws->b_counts, kBatch * nr * 4));
-    TVZ_CUDA(cudaMemset(ws->b_counts, 0, kBatch * nr * 4));
-    TVZ_CUDA(cudaMalloc(&ws->b_out, kBatch * (ws->cap + 1) * 8));
-    TVZ_CUDA(cudaMalloc(&ws->b_rows, kBatch * ws->cap * 8));
-    TVZ_CUDA(cudaMalloc(&ws->b_nhits, kBatch * 8));
-    TVZ_CUDA(cudaMalloc(&ws->b_state, kBatch * nb * 8));
-    TVZ_CUDA(cudaMemset(ws->b_state, 0, kBatch * nb * 8));
-    TVZ_CUDA(cudaMalloc(&ws->b_ticket, kBatch * 16));
-    unsigned init[kBatch * 4];
-    for (int b = 0; b < kBatch; ++b) { init[4 * b] = 0; init[4 * b + 1] = 1; init[4 * b + 2] = 0; init[4 * b + 3] = 0; }
-    TVZ_CUDA(cudaMemcpy(ws->b_ticket, init, sizeof init, cudaMemcpyHostToDevice));
-    TVZ_CUDA(cudaMalloc(&ws->b_keys, kBatch * kParamKeys * 8));
-    TVZ_CUDA(cudaMalloc(&ws->b_mult, kBatch * kParamKeys * 4));
-    TVZ_CUDA(cudaMalloc(&ws->b_nkeys, kBatch * 4));
-    TVZ_CUDA(cudaHostAlloc(&ws->hb_stage, kBatch * kParamKeys * 12 + kBatch * 4, cudaHostAllocDefault));
-    TVZ_CUDA(cudaHostAlloc(&ws->hb_out, kBatch * (ws->cap + 1) * 8, cudaHostAllocDefault));
-    TVZ_CUDA(cudaDeviceSynchronize());
-    ws->hb_cap = ws->cap;
+/* Strided device -> host copy of a slice of n fixed-size records: bytes [offset, offset + width) of every
+ * record, pitch_bytes apart on the device AND in h (same layout); sync != 0 waits for the stream.  The
+ * sharded matchers read every shard's header plus an optimistic first slice of its hits this way. */
+int tvz_copy_records_to_host(const void *d_rec, void *h_rec, int n_records, int64_t pitch_bytes, int64_t offset_bytes,
+                             int64_t width_bytes, int sync, void *stream) {
+    TVZ_REQUIRE(d_rec && h_rec && n_records >= 1 && offset_bytes >= 0 && width_bytes >= 0 &&
+                offset_bytes + width_bytes <= pitch_bytes, "bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (width_bytes)
+        TVZ_CUDA(cudaMemcpy2DAsync(static_cast<char *>(h_rec) + offset_bytes, pitch_bytes,
+                                   static_cast<const char *>(d_rec) + offset_bytes, pitch_bytes, width_bytes, n_records,
+                                   cudaMemcpyDeviceToHost, st));
+    if (sync) TVZ_CUDA(cudaStreamSynchronize(st));
     return TVZ_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
 int tvz_catalog_batch_limit(void) { return kParamKeys; }
+int tvz_catalog_batch_size(void) { return kBatch; }
 
-/* Up to 8 queries per catalogue pass; more are processed group by group.  Queries with more than
+/* Device-resident batch: up to 8 queries, records to d_out int32 [n_queries][out_cap + 1][2]. */
+int tvz_catalog_match_batch_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all, const int64_t *q_off,
+                                  int n_queries, int min_match, int32_t *d_out, int64_t out_cap, void *stream) {
+    return guarded([&]() -> int {
+    TVZ_REQUIRE(cat && ws && ws->cat == cat, "workspace does not belong to this catalogue");
+    TVZ_REQUIRE(q_off && d_out && (q_all || q_off[n_queries] == 0), "bad arguments");
+    return enqueue_batch(cat, ws, q_all, q_off, 0, n_queries, min_match, d_out, out_cap, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int tvz_catalog_match_batch_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
+                                         const int64_t *q_off, int n_queries, int min_match, int n_peers,
+                                         const uint64_t *peer_record, const uint64_t *peer_flag,
+                                         const uint32_t *d_my_flags, int64_t out_cap, uint32_t epoch, void *stream) {
+    return guarded([&]() -> int {
+    TVZ_REQUIRE(cat && ws && ws->cat == cat, "workspace does not belong to this catalogue");
+    TVZ_REQUIRE(cat->max_tiles() > 0, "the fused gather needs a non-empty shard");
+    TVZ_REQUIRE(q_off && (q_all || q_off[n_queries] == 0), "bad arguments");
+    GatherTargets gt;
+    int rc = make_gather(n_peers, peer_record, peer_flag, d_my_flags, epoch, gt);
+    if (rc) return rc;
+    return enqueue_batch(cat, ws, q_all, q_off, 0, n_queries, min_match, nullptr, out_cap, static_cast<cudaStream_t>(stream),
+                         &gt, d_my_flags);
+    });
+}
+
+/* Any number of queries, 8 per catalogue pass; host buffers in and out.  Queries with more than
  * tvz_catalog_batch_limit() distinct values are refused (run them through tvz_catalog_match). */
 int tvz_catalog_match_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all, const int64_t *q_off,
                             int n_queries, int min_match, int32_t *out_video_id, int32_t *out_count,
@@ -1319,78 +1673,31 @@ int tvz_catalog_match_batch(const tvz_catalog *cat, tvz_match_ws *ws, const doub
     TVZ_REQUIRE(cap_total >= 0 && (cap_total == 0 || (out_video_id && out_count)), "bad output buffers");
     out_off[0] = 0;
     if (n_queries == 0) return TVZ_OK;
-    int rc = ensure_batch_buffers(ws);
-    if (rc) return rc;
     cudaStream_t st = ws->stream;
-    unsigned long long *h_keys = reinterpret_cast<unsigned long long *>(ws->hb_stage);
-    int *h_mult = reinterpret_cast<int *>(h_keys + kBatch * kParamKeys);
-    int *h_nk = h_mult + kBatch * kParamKeys;
     const long long rec = (ws->cap + 1) * 2;
     long long written = 0;
     bool overflow = false;
     long long need_cap = 0, need_total = 0;
-    std::vector<unsigned long long> sorted;
     for (int g0 = 0; g0 < n_queries; g0 += kBatch) {
         const int nb = std::min(kBatch, n_queries - g0);
+        int rc = enqueue_batch(cat, ws, q_all, q_off, g0, nb, min_match, nullptr, 0, st);
+        if (rc) return rc;
+        // headers + an optimistic first slice of every query's hits in one strided copy
+        const long long first = std::min<long long>(ws->cap, 512);
+        TVZ_CUDA(cudaMemcpy2DAsync(ws->hb_out, rec * 4, ws->b_out, rec * 4, (first + 1) * 8, nb, cudaMemcpyDeviceToHost, st));
+        TVZ_CUDA(cudaStreamSynchronize(st));
+        for (bool &busy : ws->b_stage_busy) busy = false;
+        bool more = false;
         for (int b = 0; b < nb; ++b) {
-            const double *q = q_all + q_off[g0 + b];
-            const long long qn = q_off[g0 + b + 1] - q_off[g0 + b];
-            TVZ_REQUIRE(qn >= 0, "query offsets must be non-decreasing");
-            sorted.clear();
-            for (long long i = 0; i < qn; ++i) {
-                const unsigned long long bits = canon_bits(q[i]);
-                if (!is_nan_bits(bits)) sorted.push_back(bits);
+            const long long n = ws->hb_out[b * rec];
+            if (n > ws->cap) { overflow = true; need_cap = std::max(need_cap, n); continue; }
+            if (n > first) {
+                TVZ_CUDA(cudaMemcpyAsync(ws->hb_out + b * rec + 2 * (first + 1), ws->b_out + b * rec + 2 * (first + 1),
+                                         (n - first) * 8, cudaMemcpyDeviceToHost, st));
+                more = true;
             }
-            std::sort(sorted.begin(), sorted.end());
-            int nk = 0;
-            for (size_t i = 0; i < sorted.size();) {
-                size_t j = i;
-                while (j < sorted.size() && sorted[j] == sorted[i]) ++j;
-                TVZ_REQUIRE(nk < kParamKeys, "query %d has more than %d distinct values: not batchable", g0 + b,
-                            kParamKeys);
-                h_keys[b * kParamKeys + nk] = sorted[i];
-                h_mult[b * kParamKeys + nk] = static_cast<int>(j - i);
-                ++nk;
-                i = j;
-            }
-            h_nk[b] = nk;
         }
-        if (cat->n_rows > 0) {
-            TVZ_CUDA(cudaMemcpyAsync(ws->b_keys, h_keys, kBatch * kParamKeys * 8, cudaMemcpyHostToDevice, st));
-            TVZ_CUDA(cudaMemcpyAsync(ws->b_mult, h_mult, kBatch * kParamKeys * 4, cudaMemcpyHostToDevice, st));
-            TVZ_CUDA(cudaMemcpyAsync(ws->b_nkeys, h_nk, kBatch * 4, cudaMemcpyHostToDevice, st));
-            TVZ_CUDA(cudaFuncSetAttribute(match_count_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(sizeof(BatchSmem))));
-            const long long chunks = cat->n_pairs_padded / kChunkPairs;
-            const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(chunks, 2ll * num_sms())));
-            if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
-            match_count_batch_kernel<<<grid, kCountThreads, sizeof(BatchSmem), st>>>(
-                reinterpret_cast<const ulonglong2 *>(cat->d_ts), cat->n_pairs_padded, ws->b_keys, ws->b_mult, ws->b_nkeys,
-                nb, cat->d_off, cat->d_block_row, cat->n_rows, ws->b_counts, cat->n_rows);
-            TVZ_CUDA(cudaGetLastError());
-            if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
-            BatchStrides bs;
-            bs.counts = cat->n_rows;
-            bs.out = rec;
-            bs.rows = ws->cap;
-            bs.state = std::max(1, ws->n_blocks);
-            rc = compact_enqueue_batch(ws->b_counts, cat->n_rows, min_match, cat->d_vid, ws->b_out, ws->b_rows, ws->cap,
-                                       ws->b_nhits, ws->b_state, ws->b_ticket, nb, bs, st);
-            if (rc) return rc;
-            // headers of the group in one strided copy, then each query's hits
-            TVZ_CUDA(cudaMemcpy2DAsync(ws->hb_out, rec * 4, ws->b_out, rec * 4, 8, nb, cudaMemcpyDeviceToHost, st));
-            TVZ_CUDA(cudaStreamSynchronize(st));
-            for (int b = 0; b < nb; ++b) {
-                const long long n = ws->hb_out[b * rec];
-                if (n > ws->cap) { overflow = true; need_cap = std::max(need_cap, n); continue; }
-                if (n > 0)
-                    TVZ_CUDA(cudaMemcpyAsync(ws->hb_out + b * rec + 2, ws->b_out + b * rec + 2, n * 8,
-                                             cudaMemcpyDeviceToHost, st));
-            }
-            TVZ_CUDA(cudaStreamSynchronize(st));
-        } else {
-            for (int b = 0; b < nb; ++b) ws->hb_out[b * rec] = 0;
-        }
+        if (more) TVZ_CUDA(cudaStreamSynchronize(st));
         for (int b = 0; b < nb; ++b) {
             const long long n = std::min<long long>(ws->hb_out[b * rec], ws->cap);
             need_total += ws->hb_out[b * rec];

@@ -82,6 +82,21 @@ class FragmentCatalogue:
                                                 int(tol_gap), int(anchor), int(zero_offset_only), out.data_ptr(), cap,
                                                 int(st.cuda_stream)))
 
+    def match_gather_async(self, clip_timestamps, min_match: int, peer_record: np.ndarray, peer_flag: np.ndarray,
+                           my_flags_ptr: int, out_cap: int, epoch: int, tol: int = DEFAULT_TOL,
+                           tol_gap: int = DEFAULT_TOL_GAP, anchor: int = DEFAULT_ANCHOR, zero_offset_only: bool = False,
+                           stream=None) -> None:
+        """Enqueue one query whose record is stored straight into every peer's gather buffer by the
+        compaction kernel (tvz_fragcat_match_gather_async)."""
+        q = np.ascontiguousarray(np.asarray(clip_timestamps, dtype=np.float64).reshape(-1))
+        st = torch.cuda.current_stream(self.device) if stream is None else stream
+        with torch.cuda.device(self.device):
+            check(lib().tvz_fragcat_match_gather_async(self._handle, q.ctypes.data, q.shape[0], int(min_match), int(tol),
+                                                       int(tol_gap), int(anchor), int(zero_offset_only),
+                                                       int(peer_record.shape[0]), peer_record.ctypes.data,
+                                                       peer_flag.ctypes.data, int(my_flags_ptr), int(out_cap),
+                                                       int(epoch) & 0xffffffff, int(st.cuda_stream)))
+
     def find_fragments(self, clip_timestamps, min_match: int = 5, top_k: int | None = None, **kw):
         """[(video_id, score, offset_seconds)]: every stored video that contains at least `min_match`
         of the clip's cuts at one common offset.  Catalogue order, or best-first when top_k is given."""

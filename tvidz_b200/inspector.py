@@ -28,31 +28,50 @@ class Video:                                   # db.py:12-20
     duplicates: list[int] = field(default_factory=list)
 
 
+class _Request:
+    __slots__ = ("q", "min_match", "with_kth", "result", "error", "event", "promoted")
+
+    def __init__(self, q, min_match, with_kth):
+        self.q, self.min_match, self.with_kth = q, min_match, with_kth
+        self.result = self.error = None
+        self.event = threading.Event()
+        self.promoted = False
+
+
 class Inspector:
     """Videos + `video_timestamps` rows in process memory, matched on the GPU.
 
-    The packed device catalogue is immutable; row updates go to a small overlay catalogue and
-    a tombstone set so that the reference's per-cut pattern -- add_timestamps() then
-    find_duplicates() for every new cut (app.py:234-235) -- never repacks the big catalogue.
-    The overlay is folded into a fresh pack once it outgrows `overlay_limit` rows.
+    One mutable device catalogue: add_timestamps() is a device-side row upsert (the replaced row is
+    neutralised in place, the new one lands in the catalogue's tail), so the reference's per-cut
+    pattern -- add_timestamps() then find_duplicates() for every new cut (app.py:234-235) -- costs one
+    small kernel plus one query kernel and never repacks.  A repack (full pack of the host rows)
+    happens only when the tail is full of live rows.
+
+    Concurrency: the reference runs one analysis thread per upload (app.py:43,472), each calling
+    find_duplicates.  Concurrent callers are COMBINED: whoever arrives first leads, collects the
+    requests that queued up meanwhile and answers up to 8 of them with one batched pass over the
+    catalogue; then leadership moves on to the next waiting caller.  Upserts and query passes
+    exclude one another (a query never sees half an upsert).
     Result order: rows in order of their last write (the reference's own order is Postgres heap
     order, db.py:83, which also moves a row on UPDATE).
     """
 
-    def __init__(self, device: int | None = None, overlay_limit: int | None = None):
+    def __init__(self, device: int | None = None, tail_values: int | None = None, hit_capacity: int | None = None):
         self._device = device
-        self._lock = threading.RLock()
+        self._lock = threading.RLock()              # host tables
+        self._gpu = threading.Lock()                # one pass or one upsert at a time on the device catalogue
+        self._qlock = threading.Lock()              # the request queue
+        self._pending: list[_Request] = []
+        self._leader = False
         self._videos: dict[int, Video] = {}
         self._rows: dict[int, list[float]] = {}     # video_id -> timestamps, ordered by last write
         self._next_id = 1
-        self._overlay_limit = overlay_limit
-        self._main: Catalogue | None = None         # packed snapshot
-        self._main_ids: set[int] = set()
-        self._tomb: set[int] = set()                # ids in the snapshot whose row was rewritten since
-        self._overlay_rows: dict[int, list[float]] = {}
-        self._overlay: Catalogue | None = None
-        self._overlay_dirty = False
-        self.repacks = 0                            # observability: full packs of the big catalogue
+        self._tail_values = tail_values
+        self._hit_capacity = hit_capacity
+        self._cat: Catalogue | None = None          # packed snapshot + tail
+        self._stale = True                          # the device catalogue must be (re)built before the next query
+        self.repacks = 0                            # observability: full packs of the host rows
+        self.batches: list[int] = []                # observability: queries answered per device pass (last 1024)
 
     # ---------------------------------------------------------------- db.py mirror
     def add_video(self, filename, thumbnail_path=None) -> Video:          # db.py:32-41
@@ -64,15 +83,13 @@ class Inspector:
 
     def add_timestamps(self, video_id, timestamps) -> None:               # db.py:43-64 (upsert)
         row = [float(x) for x in timestamps]
-        with self._lock:
-            self._rows.pop(video_id, None)
-            self._rows[video_id] = row                                    # last write goes last
-            if self._main is not None:
-                if video_id in self._main_ids:
-                    self._tomb.add(video_id)
-                self._overlay_rows.pop(video_id, None)
-                self._overlay_rows[video_id] = row
-                self._overlay_dirty = True
+        with self._gpu:                                                   # no query pass while the row changes
+            with self._lock:
+                self._rows.pop(video_id, None)
+                self._rows[video_id] = row                                # last write goes last
+                cat = None if self._stale else self._cat
+            if cat is not None and not cat.upsert(video_id, row):
+                self._stale = True                                        # tail full: repack before the next query
 
     def update_duplicates(self, video_id, duplicate_ids) -> None:         # db.py:66-74
         with self._lock:
@@ -91,51 +108,101 @@ class Inspector:
         return None
 
     def clear_db(self) -> None:                                           # /admin/clear-db
-        with self._lock:
+        with self._gpu, self._lock:
             self._videos.clear()
             self._rows.clear()
             self._next_id = 1
-            self._drop_packs()
+            self._drop_pack()
 
-    def _drop_packs(self) -> None:
-        for c in (self._main, self._overlay):
-            if c is not None:
-                c.close()
-        self._main = self._overlay = None
-        self._main_ids, self._tomb, self._overlay_rows = set(), set(), {}
-        self._overlay_dirty = False
+    def load_rows(self, rows: Iterable[tuple[int, Sequence[float]]]) -> None:
+        """Bulk ingest of existing `video_timestamps` rows ((video_id, timestamps) pairs), e.g. the
+        table as fetched once at start-up; equivalent to add_timestamps per row."""
+        with self._gpu, self._lock:
+            for vid, ts in rows:
+                self._rows.pop(vid, None)
+                self._rows[vid] = ts if isinstance(ts, list) else [float(x) for x in ts]
+                self._next_id = max(self._next_id, int(vid) + 1)
+            self._stale = True
 
-    def _packs(self):
-        """-> (main catalogue, tombstoned ids as int32 array, overlay catalogue or None)."""
-        with self._lock:
-            limit = self._overlay_limit if self._overlay_limit is not None else max(1024, len(self._main_ids) // 64)
-            if self._main is None or len(self._overlay_rows) > limit:
-                self._drop_packs()
-                self._main = Catalogue(*rows_to_csr(self._rows.items()), device=self._device)
-                self._main_ids = set(self._rows.keys())
+    def _drop_pack(self) -> None:
+        if self._cat is not None:
+            self._cat.close()
+        self._cat = None
+        self._stale = True
+
+    def _catalogue(self) -> Catalogue:
+        """The device catalogue, (re)packed from the host rows if needed.  Called with _gpu held."""
+        if self._stale or self._cat is None:
+            with self._lock:
+                self._drop_pack()
+                n = len(self._rows)
+                tail = self._tail_values if self._tail_values is not None else max(1 << 18, 8 * n)
+                kw = {} if self._hit_capacity is None else {"hit_capacity": self._hit_capacity}
+                self._cat = Catalogue(*rows_to_csr(list(self._rows.items())), device=self._device, mutable=True,
+                                      tail_values=tail, **kw)
+                self._stale = False
                 self.repacks += 1
-            if self._overlay_dirty:
-                if self._overlay is not None:
-                    self._overlay.close()
-                self._overlay = Catalogue(*rows_to_csr(self._overlay_rows.items()), device=self._device,
-                                          hit_capacity=4096)
-                self._overlay_dirty = False
-            tomb = np.fromiter(self._tomb, np.int32, len(self._tomb))
-            return self._main, tomb, self._overlay
+        return self._cat
+
+    # ---------------------------------------------------------------- combining front door
+    def _run(self, batch: list[_Request]) -> None:
+        """Answer the requests of one device pass (all with the same min_match, none with kth unless alone)."""
+        try:
+            with self._gpu:
+                cat = self._catalogue()
+                if len(batch) == 1:
+                    r = batch[0]
+                    r.result = cat.match(r.q, r.min_match, r.with_kth)
+                else:
+                    for r, res in zip(batch, cat.match_many([r.q for r in batch], batch[0].min_match)):
+                        r.result = res
+                self.batches.append(len(batch))
+                if len(self.batches) > 1024:
+                    del self.batches[:512]
+        except BaseException as e:                  # every waiter must wake up, with the error
+            for r in batch:
+                if r.result is None:
+                    r.error = e
 
     def _match(self, new_timestamps, min_match: int, with_kth: bool = False):
-        with self._lock:        # a concurrent upsert may retire the packs: queries on one Inspector serialise
-            return self._match_locked(new_timestamps, min_match, with_kth)
-
-    def _match_locked(self, new_timestamps, min_match: int, with_kth: bool):
-        main, tomb, overlay = self._packs()
-        parts = [main.match(new_timestamps, min_match, with_kth)]
-        if tomb.size:
-            keep = ~np.isin(parts[0][0], tomb)
-            parts[0] = tuple(a[keep] for a in parts[0])
-        if overlay is not None:
-            parts.append(overlay.match(new_timestamps, min_match, with_kth))
-        return tuple(np.concatenate(cols) for cols in zip(*parts))
+        q = np.ascontiguousarray(np.asarray(new_timestamps if isinstance(new_timestamps, np.ndarray)
+                                            else list(new_timestamps), dtype=np.float64).reshape(-1))
+        req = _Request(q, int(min_match), with_kth)
+        with self._qlock:
+            self._pending.append(req)
+            lead = not self._leader
+            if lead:
+                self._leader = True
+        if not lead:
+            req.event.wait()
+            lead = req.promoted and req.result is None and req.error is None
+        if lead:
+            batch_size = 8
+            with self._qlock:
+                # the leader's own request first, then compatible ones in arrival order
+                self._pending.remove(req)
+                batch = [req]
+                if not with_kth and Catalogue.batchable(q):
+                    for r in list(self._pending):
+                        if len(batch) == batch_size:
+                            break
+                        if r.min_match == req.min_match and not r.with_kth and Catalogue.batchable(r.q):
+                            batch.append(r)
+                            self._pending.remove(r)
+            self._run(batch)
+            with self._qlock:
+                nxt = self._pending[0] if self._pending else None
+                if nxt is None:
+                    self._leader = False
+                else:
+                    nxt.promoted = True             # leadership moves on
+            for r in batch[1:]:
+                r.event.set()
+            if nxt is not None:
+                nxt.event.set()
+        if req.error is not None:
+            raise req.error
+        return req.result
 
     def find_duplicates(self, new_timestamps, min_match=5):               # db.py:76-94
         """[(video_id, match_count)] for every stored row with at least `min_match` of the
