@@ -17,13 +17,13 @@ q = ts[off[123_456]:off[123_457]].copy()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 sink = torch.zeros(1, dtype=torch.int64, device=dev)
 mhz = 1965.0
-names = ["prologue (map, keys)", "pdl wait + epoch", "stream", "drain + sync", "count + publish + prefix", "header + write"]
+names = ["zero map+counts (+td)", "keys -> map", "pdl wait + seq", "stream (warp 0)", "drain + sync", "count rows + publish", "poll predecessors", "excl + header", "write hits (thread 0)"]
 for n in sizes:
     cat = Catalogue(ts[:off[n]], off[:n + 1], vid[:n], hit_capacity=1 << 15)
     rec = torch.zeros(((1 << 15) + 1, 2), dtype=torch.int32, device=dev)
     for _ in range(3):
         cat.match_async(q, 2, rec)
-    trace = torch.zeros((cat.n_tiles, 8), dtype=torch.int64, device=dev)
+    trace = torch.zeros((cat.n_tiles, 16), dtype=torch.int64, device=dev)
     ws = cat._ws_async(0)
     for mode in ("cold", "warm"):
         check(lib().tvz_debug_tile_trace(ws.handle, trace.data_ptr()))
@@ -38,8 +38,8 @@ for n in sizes:
         check(lib().tvz_debug_tile_trace(ws.handle, None))
         t = trace.cpu().numpy().astype(np.float64)
         start_ns = t[:, 0] - t[:, 0].min()
-        d = np.diff(t[:, 1:], axis=1) / mhz * 1.0          # cycles -> us at `mhz` MHz
-        total = (t[:, 7] - t[:, 1]) / mhz
+        d = np.diff(t[:, 1:11], axis=1) / mhz * 1.0          # cycles -> us at `mhz` MHz
+        total = (t[:, 10] - t[:, 1]) / mhz
         print(f"rows {n} {mode}: event time {e0.elapsed_time(e1) * 1e3:.1f} us; CTA start spread {start_ns.max() / 1e3:.1f} us "
               f"(median {np.median(start_ns) / 1e3:.1f}); CTA lifetime median {np.median(total):.1f} max {total.max():.1f} us "
               f"(clock {mhz} MHz assumed)")

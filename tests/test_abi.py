@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 import tvidz_b200._lib as L
@@ -119,3 +120,54 @@ def test_fingerprint_layout_edge_sizes():
             idx = u * 512 + p
             want = np.where(idx < n, h[np.minimum(idx, max(n - 1, 0))] if n else 0, 0)
             assert np.array_equal(fp[u * 512:(u + 1) * 512], want), (n, kind, u)
+
+
+def _tiles(off, want):
+    import ctypes as C
+    lib = L.lib()
+    off = np.ascontiguousarray(off, np.int64)
+    out = np.zeros((20000, 4), np.int32)
+    U = C.c_int32(-1)
+    n = lib.tvz_debug_build_tiles(off.ctypes.data, off.shape[0] - 1, want, out.ctypes.data, out.shape[0], C.byref(U))
+    assert 0 <= n <= out.shape[0]
+    return out[:n], int(U.value)
+
+
+@pytest.mark.parametrize("shape", ["cfg4", "short_rows", "empty_rows", "giant_row", "tiny", "all_empty"])
+def test_tiling_covers_every_row_once(shape):
+    """The catalogue cut the matcher's CTAs work on (host only): whole rows, every row in exactly one tile,
+    at most 4096 rows per tile, and a unit range that holds every value of the tile's rows.  Regular
+    catalogues get the arithmetic ("uniform") cut, awkward ones the greedy one."""
+    rng = np.random.default_rng(3)
+    if shape == "cfg4":
+        lens = rng.integers(8, 121, 300_000)
+    elif shape == "short_rows":
+        lens = rng.integers(0, 3, 2_000_000)
+    elif shape == "empty_rows":
+        lens = np.zeros(30_000, np.int64)
+        lens[rng.integers(0, 30_000, 500)] = rng.integers(1, 90, 500)
+    elif shape == "giant_row":
+        lens = rng.integers(1, 30, 3000)
+        lens[1500] = 400_000
+    elif shape == "tiny":
+        lens = np.array([1, 1])
+    else:
+        lens = np.zeros(10, np.int64)
+    off = np.zeros(lens.shape[0] + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    for want in (295, 296, 7):
+        tiles, U = _tiles(off, want)
+        assert tiles[:, 1].max() <= 4096 and tiles[:, 1].min() >= 0
+        assert tiles[0, 0] == 0 and np.array_equal(tiles[1:, 0], tiles[:-1, 0] + tiles[:-1, 1])
+        assert tiles[-1, 0] + tiles[-1, 1] == lens.shape[0]
+        for t, (r0, nr, u0, u1) in enumerate(tiles.tolist()):
+            lo, hi = int(off[r0]), int(off[r0 + nr])
+            if hi > lo:
+                assert u0 * 512 <= lo and hi <= u1 * 512, (shape, want, t)
+            if U > 0:
+                assert u0 == t * U
+        if shape == "cfg4" and want > 7:
+            assert U > 0 and want - 2 <= len(tiles) <= want     # one wave, balanced by stored values
+            assert np.ptp(tiles[:-1, 3] - tiles[:-1, 2]) <= 2
+        if shape == "empty_rows":
+            assert U == 0                                        # thousands of rows at one offset: greedy cut

@@ -57,7 +57,7 @@ _DEBUG_SYMBOLS = [("tvz_debug_sad_tuning", _i, [_i, _i, _i, _i]),
                   ("tvz_debug_match_count_ms", _i, [_vp, C.POINTER(C.c_float)]),
                   ("tvz_debug_tile_trace", _i, [_vp, _vp]),
                   ("tvz_debug_arrange_fingerprints", _i, [_vp, _i64, _vp, _vp]),
-                  ("tvz_debug_build_tiles", _i, [_vp, _i64, _i, _vp, _i])]
+                  ("tvz_debug_build_tiles", _i, [_vp, _i64, _i, _vp, _i, _vp])]
 
 TVZ_ERR_OVERFLOW = -4
 _lib = None

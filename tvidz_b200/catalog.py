@@ -261,11 +261,13 @@ class Catalogue:
 
     @staticmethod
     def _pack_queries(queries):
-        qs = [_as_query(q) for q in queries]
-        q_off = np.zeros(len(qs) + 1, np.int64)
-        np.cumsum([q.shape[0] for q in qs], out=q_off[1:])
-        q_all = np.concatenate(qs) if q_off[-1] else np.zeros(1, np.float64)
-        return q_all, q_off
+        qs = [q if (type(q) is np.ndarray and q.dtype == np.float64 and q.ndim == 1) else _as_query(q) for q in queries]
+        q_off = np.empty(len(qs) + 1, np.int64)
+        total = q_off[0] = 0
+        for i, q in enumerate(qs):
+            total += q.shape[0]
+            q_off[i + 1] = total
+        return (np.concatenate(qs) if total else np.zeros(1, np.float64)), q_off
 
     def match_batch_async(self, queries, min_match: int, out: torch.Tensor, stream=None) -> None:
         """Up to 8 queries in one pass; `out`: int32 CUDA tensor [n_queries, cap + 1, 2]."""

@@ -53,10 +53,10 @@ constexpr int kTileRows = 4096;              // rows whose counts one CTA keeps 
 constexpr int kTileKeys = 1024;              // distinct values of ONE query kept in shared memory (more: searched in global memory)
 constexpr int kParamKeys = 224;              // distinct values that ride in the kernel parameters; per-query limit of a batch
 constexpr int kBatch = 8;                    // queries per batched pass
-constexpr int kMinTileUnits = 16;            // small catalogues: at least one unit per warp and tile
+constexpr int kMinTileUnits = 32;            // small catalogues: at least two units per warp and tile
+constexpr int kFpPadUnits = 64;              // fingerprint array padding: a tile's first (speculative) loads stay in bounds
 constexpr int kMaxTailTiles = 16;            // the mutable tail: up to 16 tiles = 65536 rows between repacks
 constexpr int kTailRows = kMaxTailTiles * kTileRows;
-constexpr int kMaxGridParam = 320;           // tiles whose unit range rides in the kernel parameters (>= 2 CTAs x 148 SMs)
 constexpr unsigned long long kPadPattern = 0x7ff8dead0000beefull;  // a NaN: never equals a stored value
 
 // Two IMADs and a shift: good enough on frame-quantised timestamps and on x.0 / x.5 values
@@ -104,10 +104,6 @@ struct alignas(16) TileDesc {
     int row_lo, n_rows;
     unsigned unit_lo, unit_hi;
 };
-struct TileUnits {                // unit range of tile t < kMaxGridParam, in the kernel parameters: the
-    unsigned lo[kMaxGridParam];   // first loads are issued before anything else is read
-    unsigned hi[kMaxGridParam];
-};
 
 template <int kQ>
 struct TileShape {
@@ -134,7 +130,6 @@ struct alignas(16) TileSmem {
     int n_keys[kQ];
     unsigned warp_tot[kQ][S::kWarps];      // qualifying rows per warp, then their exclusive prefix
     unsigned agg[kQ];
-    unsigned epoch, last;
 };
 
 struct TileArgs {
@@ -156,33 +151,23 @@ struct TileArgs {
     long long out_stride;
     long long *rows_out;                    // [cap] row index of every hit (single query; nullable)
     long long *n_hits_out;                  // [n_queries]
-    unsigned long long *state;              // [n_tiles][kQ]: {query epoch << 32 | qualifying rows of the tile}
-    unsigned *ctrl;                         // {query epoch, finished CTAs}
+    unsigned *state;                        // [n_tiles][kQ]: {query sequence << 16 | qualifying rows of the tile}
+    unsigned *ctrl;                         // {finished CTAs} (fused gather only)
+    unsigned seq;                           // this query's sequence number on its workspace (1..65535)
+    int uniform_units;                      // > 0: packed tile t starts at unit t * uniform_units (no lookup before the first loads)
     const unsigned *my_flags;               // fused gather: this rank's flags, written by the peers
-    long long *trace;                       // debug: [n_tiles][8] phase timestamps (tvz_debug_tile_trace), normally null
+    long long *trace;                       // debug: [n_tiles][16] phase timestamps (tvz_debug_tile_trace), normally null
     GatherTargets gt;
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+// L2-coherent accesses to the words CTAs exchange (no L1, no fence of their own)
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// The total of an earlier tile, once it is published for this query.  Bounded: a protocol bug must
-// surface as a launch failure, never as a hung GPU.  (Earlier tiles belong to CTAs with a lower
-// blockIdx, which the hardware dispatches first: a CTA never waits for one that is not running.)
-__device__ __forceinline__ unsigned wait_tile_total(const unsigned long long *p, unsigned epoch) {
-    unsigned polls = 0;
-    while (true) {
-        const unsigned long long r = ld_acquire_u64(p);
-        if (static_cast<unsigned>(r >> 32) == epoch) return static_cast<unsigned>(r);
-        if (++polls > 64) __nanosleep(64);
-        if (polls == (1u << 25)) __trap();
-    }
+__device__ __forceinline__ void st_relaxed_u32(unsigned *p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 template <class T>
@@ -197,8 +182,7 @@ __device__ __forceinline__ int lower_bound_u64(const T &at, int n, unsigned long
 
 template <int kQ, bool kParamQuery>
 __global__ void __launch_bounds__(TileShape<kQ>::kThreads, TileShape<kQ>::kMinBlocks)
-match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ TileUnits tu,
-                  const __grid_constant__ SmallQuery sq) {
+match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ SmallQuery sq) {
     using S = TileShape<kQ>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem<kQ> &sm = *reinterpret_cast<TileSmem<kQ> *>(smem_raw);
@@ -210,38 +194,48 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Ti
             long long t;
             if (k == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             else t = clock64();
-            a.trace[static_cast<size_t>(tile) * 8 + k] = t;
+            a.trace[static_cast<size_t>(tile) * 16 + k] = t;
         }
     };
     mark(0);
     mark(1);
 
     // ---- prologue: nothing here depends on the previous kernel of the stream ----
-    unsigned unit_lo, unit_hi;
+    // The tile descriptor is on its way while the byte map and the counts are zeroed; the first
+    // fingerprint loads follow it (they do not depend on the query either).
     const bool in_tail = a.tail_index >= 0 && tile >= a.tail_index;
-    if (in_tail) { unit_lo = a.tail[tile - a.tail_index].unit_lo; unit_hi = a.tail[tile - a.tail_index].unit_hi; }
-    else if (tile < kMaxGridParam) { unit_lo = tu.lo[tile]; unit_hi = tu.hi[tile]; }
-    else { unit_lo = a.tiles[tile].unit_lo; unit_hi = a.tiles[tile].unit_hi; }
-    const bool resident = kQ > 1 || a.n_keys <= S::kKeys;   // the query's keys fit shared memory
-    const bool scan = kQ > 1 || a.n_keys > 0;               // an empty query matches nothing: no stream
-    if (!scan) unit_hi = unit_lo;
-    // the first loads do not depend on the query: issue them before the byte map is built
-    const unsigned short *lane_fp = a.fp + lane * 16;
-    U32x8 v[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const unsigned g = unit_lo + warp + j * S::kWarps;
-        if (g < unit_hi) v[j] = ld_stream_u32x8(lane_fp + static_cast<size_t>(g) * kFpPerUnit);
-    }
+    const bool uniform = a.uniform_units > 0 && !in_tail;
     TileDesc td;
     if (in_tail) td = a.tail[tile - a.tail_index];
     else td = a.tiles[tile];
+    const bool resident = kQ > 1 || a.n_keys <= S::kKeys;   // the query's keys fit shared memory
+    const bool scan = kQ > 1 || a.n_keys > 0;               // an empty query matches nothing: no stream
+    // Packed tiles start at a unit that is pure arithmetic (tile * uniform_units), so the first
+    // fingerprint loads -- which do not depend on the query either -- leave before anything has been
+    // read; the array is padded so that they are in bounds even where a tile turns out to be shorter.
+    const unsigned unit_lo = uniform ? static_cast<unsigned>(tile) * static_cast<unsigned>(a.uniform_units) : td.unit_lo;
+    const unsigned short *lane_fp = a.fp + lane * 16;
+    U32x8 v[2];
+    if (uniform && scan) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            v[j] = ld_stream_u32x8(lane_fp + static_cast<size_t>(unit_lo + warp + j * S::kWarps) * kFpPerUnit);
+    }
     for (int i = tid; i < kMapEntries / 16; i += S::kThreads)
         reinterpret_cast<uint4 *>(sm.map)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < S::kCountWords / 4; i += S::kThreads)
         reinterpret_cast<uint4 *>(sm.counts)[i] = make_uint4(0u, 0u, 0u, 0u);
+    const unsigned unit_hi = scan ? td.unit_hi : unit_lo;
+    if (!uniform) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const unsigned g = unit_lo + warp + j * S::kWarps;
+            if (g < unit_hi) v[j] = ld_stream_u32x8(lane_fp + static_cast<size_t>(g) * kFpPerUnit);
+        }
+    }
     if (kQ > 1 && tid < kQ) sm.n_keys[tid] = tid < nq ? min(a.n_keys_g[tid], S::kKeys) : 0;
     __syncthreads();
+    mark(2);
     if (kQ == 1) {
         for (int i = tid; i < a.n_keys; i += S::kThreads) {
             const unsigned long long k = kParamQuery ? sq.keys[i] : a.keys_g[i];
@@ -266,15 +260,10 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Ti
     // the compaction will read the video ids of this tile's rows: on their way to L2 now
     if (tid * 32 < td.n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vid + td.row_lo + tid * 32));
     __syncthreads();
-    mark(2);
+    mark(3);
     pdl_wait();               // the previous query on this workspace still owns state / ctrl / out until here
     pdl_launch_dependents();  // the next kernel may run its own prologue while this one streams
-    if (tid == 0) {
-        unsigned e;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(a.ctrl) : "memory");
-        sm.epoch = e;
-    }
-    mark(3);
+    mark(4);
 
     // ---- stream the tile's fingerprints; survivors are parked per warp and verified at the end ----
     const long long pos0 = static_cast<long long>(unit_lo) * kFpPerUnit;
@@ -355,13 +344,12 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Ti
             if (gn < unit_hi) v[j] = ld_stream_u32x8(lane_fp + static_cast<size_t>(gn) * kFpPerUnit);
         }
     }
-    mark(4);
-    drain();
-    __syncthreads();   // every count of this tile is final; sm.epoch is visible
     mark(5);
+    drain();
+    __syncthreads();   // every count of this tile is final
+    mark(6);
 
     // ---- compaction of the tile's own rows ----
-    const unsigned epoch = sm.epoch;
     const int r0 = tid * S::kRowsPerThread;
     const bool want_all = a.min_match <= 0;   // then rows without any match qualify too -- except replaced ones
     auto count_of = [&](int b, int local) -> int {
@@ -381,6 +369,11 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Ti
         if (lane == 0) sm.warp_tot[b][warp] = mine;
     }
     __syncthreads();
+    // Tile totals are exchanged through L2: every tile publishes {query sequence, total}; every thread then
+    // polls its share of the PREDECESSORS' entries (relaxed loads: no fence, no L1 invalidation per poll)
+    // until they carry this query's sequence -- one round trip once they are there, no look-back chain.
+    // Only earlier tiles are waited for: they belong to CTAs with a lower blockIdx, which the hardware
+    // dispatches first, so a CTA never waits for one that is not running.
     if (warp < nq) {   // warp b: exclusive prefix of the warps' totals of query b; publish the tile's total
         const int b = warp;
         const unsigned w = lane < S::kWarps ? sm.warp_tot[b][lane] : 0u;
@@ -391,23 +384,34 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Ti
             if (lane >= o) incl += n;
         }
         if (lane < S::kWarps) sm.warp_tot[b][lane] = incl - w;
-        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);   // <= kTileRows: fits 16 bits
         if (lane == 0) {
             sm.agg[b] = total;
-            st_release_u64(&a.state[static_cast<size_t>(tile) * kQ + b], (static_cast<unsigned long long>(epoch) << 32) | total);
+            st_relaxed_u32(&a.state[static_cast<size_t>(tile) * kQ + b], (a.seq << 16) | total);
         }
     }
-    {   // hits of all earlier tiles: every thread polls its share of the predecessors -- one round trip
+    mark(7);
+    {   // hits of all earlier tiles
+        const unsigned seq = a.seq;
         const int b = tid / S::kGroup, i0 = tid - b * S::kGroup;
         unsigned long long sum = 0;
-        if (b < nq)
-            for (int i = i0; i < tile; i += S::kGroup) sum += wait_tile_total(&a.state[static_cast<size_t>(i) * kQ + b], epoch);
+        if (b < nq) {
+            for (int i = i0; i < tile; i += S::kGroup) {
+                const unsigned *p = &a.state[static_cast<size_t>(i) * kQ + b];
+                unsigned r = ld_relaxed_u32(p), polls = 0;
+                while ((r >> 16) != seq) {   // bounded: a protocol bug must surface as a launch failure, never as a hung GPU
+                    if (++polls == (1u << 24)) __trap();
+                    r = ld_relaxed_u32(p);
+                }
+                sum += r & 0xffffu;
+            }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (lane == 0) sm.part[warp] = sum;
     }
     __syncthreads();
-    mark(6);
+    mark(8);
     if (tid < nq) {
         constexpr int kWarpsPerGroup = S::kGroup / 32;
         unsigned long long e = 0;
@@ -417,11 +421,14 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Ti
             const long long total = static_cast<long long>(e) + sm.agg[tid];
             a.n_hits_out[tid] = total;
             int *o = a.out + tid * a.out_stride;
-            o[0] = total > 0x7fffffffll ? 0x7fffffff : static_cast<int>(total);
-            o[1] = total > a.cap ? 1 : 0;
+            const int2 hdr = make_int2(total > 0x7fffffffll ? 0x7fffffff : static_cast<int>(total), total > a.cap ? 1 : 0);
+            *reinterpret_cast<int2 *>(o) = hdr;
+            for (int p = 0; p < a.gt.n_peers; ++p)   // fused gather: the header travels like any hit
+                *reinterpret_cast<int2 *>(a.gt.record[p] + tid * a.gt.query_stride) = hdr;
         }
     }
     __syncthreads();
+    mark(9);
     for (int b = 0; b < nq; ++b) {
         int cnt[S::kRowsPerThread];
         int mine = 0;
@@ -454,35 +461,29 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Ti
             }
         }
     }
+    mark(10);
 
-    // ---- the CTA that finishes last starts the next epoch (and completes the fused gather) ----
+    // ---- fused gather: the CTA that finishes last raises this rank's flag on every peer ----
+    if (a.gt.n_peers == 0) return;   // (the query sequence number comes from the host: nothing to re-arm)
     __syncthreads();
-    mark(7);
-    if (tid == 0) {
-        if (a.gt.n_peers) __threadfence_system();  // this CTA's peer stores (and the local header) before it counts as done
-        else __threadfence();
-        const unsigned done = atomicAdd(a.ctrl + 1, 1u);
-        sm.last = done == gridDim.x - 1;
+    mark(11);
+    if (warp != 0) return;
+    unsigned last = 0;
+    if (lane == 0) {
+        __threadfence_system();  // this CTA's peer stores before it counts as done
+        last = atomicAdd(a.ctrl, 1u) == gridDim.x - 1;
+        if (last) a.ctrl[0] = 0;
     }
-    __syncthreads();
-    if (!sm.last) return;
-    if (tid == 0) {
-        a.ctrl[1] = 0;
-        a.ctrl[0] = epoch + 1u ? epoch + 1u : 1u;   // state[] starts zeroed: epoch 0 is never used
-    }
-    if (a.gt.n_peers == 0) return;
-    if (tid < a.gt.n_peers) {
-        __threadfence_system();
-        for (int b = 0; b < nq; ++b) {
-            const volatile int *o = a.out + b * a.out_stride;
-            *reinterpret_cast<int2 *>(a.gt.record[tid] + b * a.gt.query_stride) = make_int2(o[0], o[1]);  // {n_hits, overflow}
-        }
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.gt.flag[tid]), "r"(a.gt.epoch) : "memory");
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    if (lane < a.gt.n_peers) {
+        // every CTA fenced its peer stores at system scope before it counted as done, and this warp has
+        // seen all of them count: the release below makes the whole record visible before the flag
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.gt.flag[lane]), "r"(a.gt.epoch) : "memory");
         // ... and wait until every peer's record for this epoch has landed here (bounded, see above)
         unsigned f, polls = 0;
         do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(a.my_flags + tid) : "memory");
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(a.my_flags + lane) : "memory");
             if (f == a.gt.epoch) break;
             __nanosleep(64);
             if (++polls == (1u << 26)) __trap();
@@ -587,7 +588,7 @@ struct tvz_catalog {
     unsigned char *d_dead = nullptr;
     TileDesc *d_tiles = nullptr;
     std::vector<TileDesc> tiles;             // tiles of the packed rows
-    TileUnits units{};
+    int uniform_units = 0;                   // > 0: packed tile t starts at unit t * uniform_units
     int tail_index = -1;
     // ---- mutable tail (tvz_catalog_upsert); everything below is guarded by `mu` ----
     mutable std::mutex mu;
@@ -616,8 +617,9 @@ struct tvz_catalog {
 struct tvz_match_ws {
     const tvz_catalog *cat = nullptr;
     long long cap = 0;
-    unsigned long long *d_state = nullptr;  // [n_tiles][kBatch] tile totals {epoch, count}
-    unsigned *d_ctrl = nullptr;             // {query epoch, finished CTAs}
+    unsigned *d_state = nullptr;            // [tiles][kBatch] {query sequence << 16 | qualifying rows of the tile}
+    unsigned *d_ctrl = nullptr;             // {finished CTAs}: fused gather, zero between queries
+    unsigned seq = 0;                       // sequence number of the last query enqueued (1..65535, 0 = none yet)
     int *d_out = nullptr;                   // [cap+1][2]
     long long *d_rows = nullptr;            // [cap]
     int *d_kth = nullptr;                   // [cap]
@@ -636,6 +638,7 @@ struct tvz_match_ws {
     bool timing = false;           // debug: bracket the kernel with events
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     long long *d_trace = nullptr;           // debug (not owned)
+    int seen_tiles = 0;                     // largest grid a query of this workspace has launched
     unsigned long long seen_mut = 0;        // last catalogue mutation a stream of this workspace has waited for
     cudaStream_t seen_stream = nullptr;     // ... and which stream that was
     // batched queries (allocated on first use)
@@ -737,12 +740,44 @@ void arrange_fingerprints(const unsigned long long *ts, long long n_vals, long l
 
 // Cut rows [0, n_rows) into tiles of whole rows: at most kTileRows rows each, about the same number of
 // stored values each, about `want` tiles (one wave of CTAs; a multiple of it when rows are short).
-void build_tiles(const std::vector<long long> &off, long long n_rows, int want, std::vector<TileDesc> &tiles) {
+// Preferred form ("uniform", returns U > 0): tile t owns the rows whose first value lies in units
+// [t * U, (t + 1) * U) -- its first unit is arithmetic, and it streams on to the end of its last row.
+// Catalogues that cannot be cut that way with <= kTileRows rows per tile (e.g. thousands of empty rows in one
+// place) fall back to a greedy cut with explicit unit ranges (returns 0).
+int build_tiles(const std::vector<long long> &off, long long n_rows, int want, std::vector<TileDesc> &tiles) {
     tiles.clear();
-    if (n_rows <= 0) return;
+    if (n_rows <= 0) return 0;
     const long long n_vals = off[n_rows];
+    const long long n_units = (n_vals + kFpPerUnit - 1) / kFpPerUnit;
     const long long by_rows = (n_rows + kTileRows - 1) / kTileRows;
     const long long waves = std::max<long long>(1, (by_rows + want - 1) / want);
+    long long U = std::max<long long>(kMinTileUnits, (n_units + waves * want - 1) / (waves * want));
+    for (int attempt = 0; attempt < 24 && n_units > 0; ++attempt) {
+        const long long T = (n_units + U - 1) / U;
+        if (T > 16ll * want) break;
+        const long long W = U * kFpPerUnit;
+        tiles.clear();
+        bool ok = true;
+        long long r = 0;
+        for (long long t = 0; t < T && ok; ++t) {
+            // rows whose first value lies below (t + 1) * W; the last tile takes whatever is left (trailing empty rows)
+            const long long e = t == T - 1 ? n_rows
+                                           : std::lower_bound(off.begin() + r, off.begin() + n_rows, (t + 1) * W) - off.begin();
+            if (e - r > kTileRows) { ok = false; break; }
+            TileDesc d;
+            d.row_lo = static_cast<int>(r);
+            d.n_rows = static_cast<int>(e - r);
+            d.unit_lo = static_cast<unsigned>(t * U);
+            d.unit_hi = e > r && off[e] > off[r] ? static_cast<unsigned>((off[e] + kFpPerUnit - 1) / kFpPerUnit) : d.unit_lo;
+            tiles.push_back(d);
+            r = e;
+        }
+        if (ok) return static_cast<int>(U);
+        if (U == kMinTileUnits) break;
+        U = std::max<long long>(kMinTileUnits, U * 3 / 4);
+    }
+    // greedy fallback
+    tiles.clear();
     const long long target = std::max<long long>(static_cast<long long>(kMinTileUnits) * kFpPerUnit,
                                                  (n_vals + waves * want - 1) / (waves * want));
     long long r = 0;
@@ -760,13 +795,7 @@ void build_tiles(const std::vector<long long> &off, long long n_rows, int want, 
         tiles.push_back(t);
         r = e;
     }
-}
-
-void fill_units(tvz_catalog *c) {
-    for (size_t t = 0; t < c->tiles.size() && t < static_cast<size_t>(kMaxGridParam); ++t) {
-        c->units.lo[t] = c->tiles[t].unit_lo;
-        c->units.hi[t] = c->tiles[t].unit_hi;
-    }
+    return 0;
 }
 
 // Tail tile k holds tail rows [k * 4096, (k + 1) * 4096) and the units their values span (tail rows are
@@ -859,11 +888,21 @@ void base_args(const tvz_catalog *cat, tvz_match_ws *ws, const CatView &cv, Tile
     a.state = ws->d_state;
     a.ctrl = ws->d_ctrl;
     a.n_hits_out = ws->d_nhits;
+    a.uniform_units = cat->uniform_units;
     a.trace = ws->d_trace;
+    ws->seq = ws->seq >= 0xffffu ? 1u : ws->seq + 1u;   // never 0: that is what fresh state[] entries carry
+    a.seq = ws->seq;
 }
 
-// A query must see every upsert that returned before it was enqueued.
+// A query must see every upsert that returned before it was enqueued.  (Also: tiles that appear for the
+// first time -- the tail has grown -- start from untagged exchange entries.)
 int wait_for_mutations(const tvz_catalog *cat, tvz_match_ws *ws, const CatView &cv, cudaStream_t st) {
+    if (cv.n_tiles > ws->seen_tiles) {
+        if (ws->seen_tiles > 0)
+            TVZ_CUDA(cudaMemsetAsync(ws->d_state + static_cast<size_t>(ws->seen_tiles) * kBatch, 0,
+                                     static_cast<size_t>(cv.n_tiles - ws->seen_tiles) * kBatch * 4, st));
+        ws->seen_tiles = cv.n_tiles;
+    }
     if (cat->tail_index >= 0 && cv.seq != 0 && (cv.seq != ws->seen_mut || st != ws->seen_stream)) {
         TVZ_CUDA(cudaStreamWaitEvent(st, cat->mut_event, 0));
         ws->seen_mut = cv.seq;
@@ -951,9 +990,9 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
             SmallQuery sq;
             memcpy(sq.keys, h_keys, sizeof(unsigned long long) * nk);
             memcpy(sq.mult, h_mult, sizeof(int) * nk);
-            TVZ_CUDA(launch_pdl(match_tile_kernel<1, true>, grid, block, sizeof(TileSmem<1>), st, a, cat->units, sq));
+            TVZ_CUDA(launch_pdl(match_tile_kernel<1, true>, grid, block, sizeof(TileSmem<1>), st, a, sq));
         } else {
-            TVZ_CUDA(launch_pdl(match_tile_kernel<1, false>, grid, block, sizeof(TileSmem<1>), st, a, cat->units, SmallQuery{}));
+            TVZ_CUDA(launch_pdl(match_tile_kernel<1, false>, grid, block, sizeof(TileSmem<1>), st, a, SmallQuery{}));
         }
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
         if (want_kth) {
@@ -1061,7 +1100,7 @@ int enqueue_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
     }
     if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
     TVZ_CUDA(launch_pdl(match_tile_kernel<kBatch, false>, dim3(static_cast<unsigned>(cv.n_tiles)),
-                        dim3(TileShape<kBatch>::kThreads), sizeof(TileSmem<kBatch>), st, a, cat->units, SmallQuery{}));
+                        dim3(TileShape<kBatch>::kThreads), sizeof(TileSmem<kBatch>), st, a, SmallQuery{}));
     if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
     return TVZ_OK;
 }
@@ -1124,12 +1163,11 @@ int catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_vi
 
     // one wave of CTAs (2 per SM), one of them kept for the tail tile
     const int want = std::max(1, 2 * num_sms() - (is_mutable ? 1 : 0));
-    build_tiles(off, n_rows, want, c->tiles);
+    c->uniform_units = build_tiles(off, n_rows, want, c->tiles);
     if (is_mutable) {
         c->tail_index = static_cast<int>(c->tiles.size());
         c->h_off = off;
     }
-    fill_units(c);
 
     // 16-bit fingerprints, padded to whole warp units (pad entries point past n_vals and are dropped)
     const size_t n_pos_main = static_cast<size_t>(std::max<long long>(1, c->n_units_main)) * kFpPerUnit;
@@ -1168,8 +1206,10 @@ int catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_vi
     };
     cudaError_t e;
     const size_t n_pos_all = static_cast<size_t>(std::max<long long>(1, n_units_all)) * kFpPerUnit;
+    const size_t n_fp_alloc = n_pos_all + static_cast<size_t>(kFpPadUnits) * kFpPerUnit;
     const size_t n_ts_all = static_cast<size_t>(std::max<long long>(1, c->ts_main_padded + c->tail_cap_vals));
-    if ((e = cudaMalloc(&c->d_fp, n_pos_all * 2)) != cudaSuccess) return fail(e, "cudaMalloc(fp)");
+    if ((e = cudaMalloc(&c->d_fp, n_fp_alloc * 2)) != cudaSuccess) return fail(e, "cudaMalloc(fp)");
+    if ((e = cudaMemset(c->d_fp, 0, n_fp_alloc * 2)) != cudaSuccess) return fail(e, "cudaMemset(fp)");
     if ((e = cudaMalloc(&c->d_rec, n_pos_all * sizeof(VerifyRec))) != cudaSuccess) return fail(e, "cudaMalloc(rec)");
     if ((e = cudaMalloc(&c->d_ts, n_ts_all * 8)) != cudaSuccess) return fail(e, "cudaMalloc(ts)");
     if ((e = cudaMalloc(&c->d_off, (rows_cap + 1) * 8)) != cudaSuccess) return fail(e, "cudaMalloc(off)");
@@ -1452,9 +1492,10 @@ int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_
         return bail(e, "cudaStreamCreate");
     cudaStream_t st = ws->stream;
     const size_t n_state = static_cast<size_t>(std::max<long long>(1, cat->max_tiles())) * kBatch;
-    if ((e = cudaMalloc(&ws->d_state, n_state * 8)) != cudaSuccess) return bail(e, "cudaMalloc(state)");
-    if ((e = cudaMemsetAsync(ws->d_state, 0, n_state * 8, st)) != cudaSuccess) return bail(e, "cudaMemset(state)");
+    if ((e = cudaMalloc(&ws->d_state, n_state * 4)) != cudaSuccess) return bail(e, "cudaMalloc(state)");
+    if ((e = cudaMemsetAsync(ws->d_state, 0, n_state * 4, st)) != cudaSuccess) return bail(e, "cudaMemset(state)");
     if ((e = cudaMalloc(&ws->d_ctrl, 8)) != cudaSuccess) return bail(e, "cudaMalloc(ctrl)");
+    if ((e = cudaMemsetAsync(ws->d_ctrl, 0, 8, st)) != cudaSuccess) return bail(e, "cudaMemset(ctrl)");
     if ((e = cudaMalloc(&ws->d_out, (ws->cap + 1) * 8)) != cudaSuccess) return bail(e, "cudaMalloc(out)");
     if ((e = cudaMemsetAsync(ws->d_out, 0, 8, st)) != cudaSuccess) return bail(e, "cudaMemset(out)");
     if ((e = cudaMalloc(&ws->d_rows, ws->cap * 8)) != cudaSuccess) return bail(e, "cudaMalloc(rows)");
@@ -1469,11 +1510,6 @@ int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_
         return bail(e, "cudaEventCreate");
     int rc = ensure_query_capacity(ws, 256);
     if (rc) { tvz_match_ws_destroy(ws); return rc; }
-    // {query epoch = 1, finished CTAs = 0} through the pinned staging buffer, on the workspace's own stream
-    reinterpret_cast<unsigned *>(ws->h_stage)[0] = 1u;
-    reinterpret_cast<unsigned *>(ws->h_stage)[1] = 0u;
-    if ((e = cudaMemcpyAsync(ws->d_ctrl, ws->h_stage, 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-        return bail(e, "cudaMemcpy(ctrl)");
     // queries may run on other streams: the initialisation must have landed before the first one
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");
     *out = ws;
@@ -1516,7 +1552,7 @@ int tvz_debug_match_timing(tvz_match_ws *ws, int enable) {
     ws->timing = enable != 0;
     return TVZ_OK;
 }
-int tvz_debug_tile_trace(tvz_match_ws *ws, long long *d_trace) {   // int64 [tiles][8] on the device, or NULL to stop
+int tvz_debug_tile_trace(tvz_match_ws *ws, long long *d_trace) {   // int64 [tiles][16] on the device, or NULL to stop
     TVZ_REQUIRE(ws, "null workspace");
     ws->d_trace = d_trace;
     return TVZ_OK;
@@ -1542,10 +1578,12 @@ int tvz_debug_arrange_fingerprints(const double *values, int64_t n, uint16_t *fp
 
 // Debug hook (host only): the tiling of a catalogue with the given CSR offsets for `want` tiles.
 // tiles_out: int32 [max_tiles][4] = {row_lo, n_rows, unit_lo, unit_hi}; returns the number of tiles.
-int tvz_debug_build_tiles(const int64_t *off, int64_t n_rows, int want, int32_t *tiles_out, int max_tiles) {
+int tvz_debug_build_tiles(const int64_t *off, int64_t n_rows, int want, int32_t *tiles_out, int max_tiles,
+                          int32_t *uniform_units_out) {
     std::vector<long long> o(off, off + n_rows + 1);
     std::vector<TileDesc> t;
-    build_tiles(o, n_rows, std::max(1, want), t);
+    const int U = build_tiles(o, n_rows, std::max(1, want), t);
+    if (uniform_units_out) *uniform_units_out = U;
     for (size_t i = 0; i < t.size() && static_cast<int>(i) < max_tiles; ++i) {
         tiles_out[4 * i] = t[i].row_lo;
         tiles_out[4 * i + 1] = t[i].n_rows;
