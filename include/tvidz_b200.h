@@ -90,6 +90,37 @@ int tvz_scene_score_host(const uint8_t *h_luma, int n_streams, int n_frames, int
                          int bitdepth, double threshold, int chunk_frames,
                          uint64_t *h_sad, double *h_score, uint8_t *h_selected);
 
+/* ------------------------------------------------------------------ decode front-end
+ * Replaces the software decode inside the ffmpeg process of inspector/app.py:202-208: demuxed packets
+ * go to the GPU's hardware decoder (NVDEC, through the driver's libnvcuvid.so.1, loaded at run time),
+ * the luma plane of every decoded frame lands in a dense ring in device memory -- the plane FFmpeg's
+ * scene filter reads for 4:2:0 sources -- and tvz_sad_luma_u8 / _u16 score it there: raw frames never
+ * cross PCIe.  There is no software fallback: without the library every call fails with a message.
+ */
+typedef enum tvz_codec {
+    TVZ_CODEC_MPEG2 = 1, TVZ_CODEC_MPEG4 = 2, TVZ_CODEC_H264 = 3, TVZ_CODEC_HEVC = 4,
+    TVZ_CODEC_VP8 = 5, TVZ_CODEC_VP9 = 6, TVZ_CODEC_AV1 = 7
+} tvz_codec;
+typedef struct tvz_decoder tvz_decoder;
+int tvz_nvdec_available(void);                                   /* 1, or 0 with tvz_last_error() saying why */
+const char *tvz_nvdec_library(void);                             /* the libnvcuvid that was loaded ("" = none) */
+/* out4 = { supported, max coded width, max coded height, NVDEC engines } for 4:2:0 at `bitdepth` */
+int tvz_nvdec_caps(int codec, int bitdepth, int32_t *out4);
+int tvz_decoder_create(int codec, int64_t ring_frames, tvz_decoder **out);
+void tvz_decoder_destroy(tvz_decoder *dec);
+/* One demuxed packet (a frame of the elementary stream; H.264/HEVC in Annex-B form) -> parser -> NVDEC.
+ * size 0 with end_of_stream != 0 flushes.  *frames_total = frames complete in the ring so far (display
+ * order); the caller consumes [consumed, *frames_total) before the ring wraps over them (one packet
+ * adds at most the decoder's surface count, <= 24 frames). */
+int tvz_decoder_feed(tvz_decoder *dec, const uint8_t *packet, int64_t size, int64_t pts, int end_of_stream,
+                     int64_t *frames_total);
+/* out6 = { width, height, bitdepth, ring_frames, frames decoded, decode surfaces }; width == 0 until the
+ * first sequence header has been parsed.  The ring is [ring_frames][height][width] samples (uint8, or
+ * uint16 with the sample in the high bits when bitdepth > 8), dense; frame n sits in slot n % ring_frames. */
+int tvz_decoder_info(const tvz_decoder *dec, int64_t *out6);
+const uint8_t *tvz_decoder_ring(const tvz_decoder *dec);          /* device pointer */
+int tvz_decoder_pts(const tvz_decoder *dec, int64_t first, int64_t n, int64_t *out);
+
 /* ------------------------------------------------------------------ stage 2
  * Replaces inspector/db.py:76-94 find_duplicates over the rows of
  * `video_timestamps` (db.py:22-27: one float8[] per video).

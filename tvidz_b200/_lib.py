@@ -19,6 +19,15 @@ SYMBOLS = [
     ("tvz_sad_luma_u8_path", _i, [_vp, _i, _i, _i64, _i64, _i64]),
     ("tvz_scene_select", _i, [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp]),
     ("tvz_scene_score_host", _i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i, _d, _i, _vp, _vp, _vp]),
+    ("tvz_nvdec_available", _i, []),
+    ("tvz_nvdec_library", C.c_char_p, []),
+    ("tvz_nvdec_caps", _i, [_i, _i, _vp]),
+    ("tvz_decoder_create", _i, [_i, _i64, C.POINTER(_vp)]),
+    ("tvz_decoder_destroy", None, [_vp]),
+    ("tvz_decoder_feed", _i, [_vp, _vp, _i64, _i64, _i, C.POINTER(_i64)]),
+    ("tvz_decoder_info", _i, [_vp, _vp]),
+    ("tvz_decoder_ring", _vp, [_vp]),
+    ("tvz_decoder_pts", _i, [_vp, _i64, _i64, _vp]),
     ("tvz_catalog_create", _i, [_vp, _vp, _vp, _i64, C.POINTER(_vp)]),
     ("tvz_catalog_create_mutable", _i, [_vp, _vp, _vp, _i64, _i64, C.POINTER(_vp)]),
     ("tvz_catalog_destroy", None, [_vp]),

@@ -153,9 +153,10 @@ class StreamScorer:
     the last frame of each stream (one D2D copy) and its SAD are carried.
     """
 
-    def __init__(self, threshold: float = DEFAULT_THRESHOLD, width: int | None = None):
+    def __init__(self, threshold: float = DEFAULT_THRESHOLD, width: int | None = None, bitdepth: int | None = None):
         self.threshold = float(threshold)
         self.width = width
+        self.bitdepth = bitdepth    # None: 8 for uint8 chunks, 10 for 16-bit ones (as score_frames)
         self._pair = None           # [S, 2, H, P]: slot 0 = carried frame, slot 1 = first frame of the new chunk
         self._last_sad = None       # int64 [S]: SAD of the last frame fed (its mafd is the next prev_mafd)
         self.frames_seen = 0
@@ -169,17 +170,22 @@ class StreamScorer:
             z = torch.zeros((S, 0), device=chunk.device)
             return z.long(), z.double(), z.to(torch.uint8)
         W = P if self.width is None else int(self.width)
+        bitdepth = self.bitdepth if self.bitdepth is not None else (8 if chunk.element_size() == 1 else 10)
+        if (bitdepth == 8) != (chunk.element_size() == 1):
+            raise ValueError("bitdepth 8 goes with uint8 frames, 9..16 with 16-bit frames")
+        if self._pair is not None and self._pair.dtype != chunk.dtype:
+            raise TypeError("the sample type changed between chunks")
         sad = sad_luma(chunk, W)                                  # [S, n], column 0 = 0 for now
         if self._pair is None:                                    # first chunk: frame 0 has no predecessor
-            self._pair = torch.empty((S, 2, H, P), dtype=torch.uint8, device=chunk.device)
-            score, sel = scene_select(sad, W, H, self.threshold)
+            self._pair = torch.empty((S, 2, H, P), dtype=chunk.dtype, device=chunk.device)
+            score, sel = scene_select(sad, W, H, self.threshold, bitdepth)
         else:
             self._pair[:, 1].copy_(chunk[:, 0])
             sad[:, 0] = sad_luma(self._pair, W)[:, 1]             # carried frame vs first new frame
             # two leading columns: a dummy "frame 0", then the carried frame's SAD, whose mafd is the
             # prev_mafd of this chunk's first frame (prev_mafd is updated on every frame, A.3)
             ext = torch.cat([torch.zeros_like(sad[:, :1]), self._last_sad[:, None], sad], dim=1)
-            score, sel = scene_select(ext, W, H, self.threshold)
+            score, sel = scene_select(ext, W, H, self.threshold, bitdepth)
             score, sel = score[:, 2:].contiguous(), sel[:, 2:].contiguous()
         self._pair[:, 0].copy_(chunk[:, -1])
         self._last_sad = sad[:, -1].clone()
