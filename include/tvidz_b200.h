@@ -241,9 +241,10 @@ const int64_t *tvz_match_ws_nhits(const tvz_match_ws *ws);
  * implements only offset-0 exact membership (inspector/db.py:78-79), so the
  * semantics are this library's own (tvidz_b200/csrc/fragment.cu header):
  *   ticks = llround(ts * tick_hz); candidate offsets d = C[j] - Q[i] come from
- *   positions where `anchor_intervals` (1..3) consecutive intervals of row and query agree
- *   within tol_gap ticks (1 = any agreeing adjacent pair; 2 = two in a row, far fewer candidates:
- *   the catalogue is then streamed once at HBM speed);
+ *   positions where `anchor_intervals` (0..3) consecutive intervals of row and query agree
+ *   within tol_gap ticks (0 = every pair (i, j): SURVEY.md B.4 as written, exhaustive and slow;
+ *   1 = any agreeing adjacent pair; 2 = two in a row, far fewer candidates: the catalogue is
+ *   then streamed once at HBM speed);
  *   score(d) = #{i : some C[j] within tol ticks of Q[i] + d}; a row reports its
  *   best (score, d) -- ties: smaller |d|, then smaller d -- iff score >= min_match.
  *   zero_offset_only = 1 scores d = 0 alone; with tol 0 that is find_duplicates'

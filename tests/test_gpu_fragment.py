@@ -35,7 +35,7 @@ def test_clip_is_found_at_its_offset(cuda):
     cat.close()
 
 
-@pytest.mark.parametrize("anchor", [1, 2, 3])
+@pytest.mark.parametrize("anchor", [0, 1, 2, 3])          # 0 = every offset C[j] - Q[i] (SURVEY.md B.4 as written)
 @pytest.mark.parametrize("min_match", [2, 3, 5])
 def test_matches_oracle_all_rows(cuda, min_match, anchor):
     ts, off, vid = _long_catalogue(1500, seed=5)
@@ -46,6 +46,11 @@ def test_matches_oracle_all_rows(cuda, min_match, anchor):
     want = oracle.find_fragments_csr(ts, off, vid, q, min_match=min_match, anchor=anchor)
     assert list(zip(v.tolist(), s.tolist(), d.tolist())) == want
     assert len(want) > 1 or min_match == 5 or anchor > 1
+    if anchor == 0:      # the anchored modes can only lose candidates: their hits are a subset with no higher score
+        for a in (1, 2, 3):
+            sub = dict((v2, s2) for v2, s2, _ in oracle.find_fragments_csr(ts, off, vid, q, min_match=min_match, anchor=a))
+            full = dict((v2, s2) for v2, s2, _ in want)
+            assert all(v2 in full and full[v2] >= s2 for v2, s2 in sub.items())
     assert (int(vid[77]), len(q)) in list(zip(v.tolist(), s.tolist()))
     cat.close()
 
@@ -108,7 +113,7 @@ def test_short_rows_tolerances_and_edges(cuda):
     q = [0.5, 1.0, 2.5, 4.0]
     for tol, tol_gap in ((0, 0), (2, 4), (7, 14)):
         for mm in (0, 1, 2, 4):
-            for anchor in (1, 2, 3):
+            for anchor in (0, 1, 2, 3):
                 v, s, d = cat.match(q, mm, tol=tol, tol_gap=tol_gap, anchor=anchor)
                 assert list(zip(v.tolist(), s.tolist(), d.tolist())) == \
                     oracle.find_fragments_csr(ts, off, vid, q, min_match=mm, tol=tol, tol_gap=tol_gap,

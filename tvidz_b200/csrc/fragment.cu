@@ -8,8 +8,10 @@
 //   * rows and the query are sets of ticks, sorted ascending, duplicates removed;
 //   * a candidate offset d = C[j] - Q[i] is generated wherever `anchor` CONSECUTIVE intervals
 //     agree:  | (C[j+a+1]-C[j+a]) - (Q[i+a+1]-Q[i+a]) | <= tol_gap  for a = 0 .. anchor-1
-//     (anchor = 1: every agreeing pair of adjacent cuts, the most permissive; anchor = 2, the
-//     default of the Python API: two agreeing intervals in a row, i.e. three cuts);
+//     (anchor = 0: EVERY pair (i, j) is a candidate -- SURVEY.md B.4 exactly as written, the
+//     exhaustive mode the anchored ones are measured against (DESIGN.md recall table);
+//     anchor = 1: every agreeing pair of adjacent cuts; anchor = 2, the default of the Python API:
+//     two agreeing intervals in a row, i.e. three cuts);
 //   * score(d) = #{ i : exists j with | Q[i] + d - C[j] | <= tol };
 //   * the row's verdict is the candidate with the highest score (ties: smaller |d|, then
 //     smaller d); the row is reported iff that score >= min_match, as
@@ -49,7 +51,7 @@ constexpr int kMaxBuckets = 2048;   // interval buckets (bucket width = power of
 constexpr int kSpan = 64;           // row intervals per lane per pass (one 64-bit hit mask)
 
 struct FragQuery {
-    int qn, tol, tol_gap, zero_only, min_match;
+    int qn, tol, tol_gap, zero_only, min_match, exhaustive;
     int q[kFragMaxQ];
 };
 
@@ -197,6 +199,18 @@ fragment_match_kernel(const int *__restrict__ ticks, const long long *__restrict
         if (qn > 0 && L > 0) {
             if (fq.zero_only) {
                 if (lane == 0) best = Best{score_offset(C, L, sm.q, qn, 0, tol), 0};
+            } else if (fq.exhaustive) {
+                // SURVEY.md B.4 as written: EVERY offset d = C[j] - Q[i] is a candidate.  A lane takes row
+                // cuts j = lane, lane + 32, ...; a walk is abandoned (exactly) once it cannot reach
+                // max(min_match, best so far).
+                for (int j = lane; j < L; j += 32) {
+                    const int c0 = __ldg(C + j);
+                    for (int i = 0; i < qn; ++i) {
+                        const int d = c0 - sm.q[i];
+                        const int s = score_anchored(C, L, sm.q, qn, d, tol, i, j, max(fq.min_match, best.score));
+                        if (better(s, d, best)) best = Best{s, d};
+                    }
+                }
             } else if (ng > 0) {
                 for (int base = 0; base < L - 1; base += 32 * kSpan) {
                     // pass 1 (branch free): which of this lane's intervals fall in a non-empty bucket
@@ -579,7 +593,7 @@ int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int t
                  int zero_only, int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr) {
     TVZ_REQUIRE(qn >= 0 && (qn == 0 || h_q), "bad query");
     TVZ_REQUIRE(tol >= 0 && tol_gap >= 0, "negative tolerance");
-    TVZ_REQUIRE(anchor >= 1 && anchor <= kMaxAnchor, "anchor_intervals must be 1..%d", kMaxAnchor);
+    TVZ_REQUIRE(anchor >= 0 && anchor <= kMaxAnchor, "anchor_intervals must be 0 (exhaustive) .. %d", kMaxAnchor);
     FragQuery fq{};
     std::vector<int> q;
     q.reserve(qn);
@@ -595,6 +609,7 @@ int frag_enqueue(tvz_fragcat *c, const double *h_q, int qn, int min_match, int t
     fq.tol = tol;
     fq.tol_gap = tol_gap;
     fq.zero_only = zero_only;
+    fq.exhaustive = anchor == 0 && !zero_only;
     std::copy(q.begin(), q.end(), fq.q);
     if (c->n_rows == 0) {
         TVZ_REQUIRE(!gather, "an empty shard cannot take part in the fused gather");
