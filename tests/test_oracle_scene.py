@@ -116,3 +116,31 @@ def test_score_sequence_random_vs_numpy():
         assert score[t] == want and sel[t] == (want > 0.3)
         prev = mafd
     assert score[0] == 0.0
+
+
+def test_scene_golden_from_ffmpeg():
+    """Stage 1 against a REAL FFmpeg: tests/golden/scene_golden.json holds lavfi.scene_score of every frame and the
+    pts_time tokens the reference's own command prints (scripts/gen_scene_golden.py writes it wherever an ffmpeg
+    binary exists -- there is none in this image or on the GPU boxes, so until then this test is skipped and
+    stage 1 stays "parity unpinned")."""
+    import json
+    import os
+    import sys
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scene_golden.json")
+    if not os.path.exists(path):
+        pytest.skip("no tests/golden/scene_golden.json: no ffmpeg binary has been reachable (stage 1 parity unpinned)")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import gen_scene_golden
+    with open(path) as f:
+        gold = json.load(f)
+    for c in gold["cases"]:
+        luma = gen_scene_golden.clip(c["seed"], c["frames"], c["width"], c["height"])
+        _, score, sel, _ = oracle.scene_batch(luma[None])
+        assert [float("%f" % s) for s in score[0]] == [float("%f" % s) for s in c["scores"]], c["seed"]   # metadata=print is "%f"
+        want = []
+        for tok in c["pts_time_tokens"]:                       # app.py:230-232
+            ts = float(tok)
+            if not want or ts != want[-1]:
+                want.append(ts)
+        fmt = 1 if any(len(t.split(".")[-1]) > 5 and float(t) >= 1 for t in c["pts_time_tokens"]) else 0
+        assert oracle.cut_timestamps(sel[0], 1, 30, fmt) == want, c["seed"]

@@ -1244,9 +1244,11 @@ int catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_vi
         if ((e = cudaEventCreateWithFlags(&c->mut_event, cudaEventDisableTiming)) != cudaSuccess)
             return fail(e, "cudaEventCreate");
         c->tail_vals.reserve(static_cast<size_t>(c->tail_cap_vals));
-        // video ids of the packed rows are needed to find the row an upsert replaces
-        c->row_of_vid.clear();
-        c->row_map_built = false;
+        // the row an upsert replaces is found by video id: index the packed rows now (first row wins,
+        // db.py:47 .first()), not inside the first upload's first add_timestamps()
+        c->row_of_vid.reserve(static_cast<size_t>(n_rows) * 2 + 1024);
+        for (long long r = 0; r < n_rows; ++r) c->row_of_vid.emplace(h_video_id[r], r);
+        c->row_map_built = true;
     }
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(e, "cudaDeviceSynchronize");
     *out = c;

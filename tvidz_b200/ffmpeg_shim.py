@@ -130,10 +130,14 @@ def y4m_frames(path: str) -> tuple[int, int, Fraction, Iterator[np.ndarray]]:
     return w, h, fps, it()
 
 
-def cv2_frames(path: str) -> tuple[int, int, Fraction, Iterator[np.ndarray]]:
-    """Luma planes through OpenCV's bundled libavcodec (software decode on the host, as in the reference)."""
+def cv2_frames(path: str, decode_threads: int | None = None) -> tuple[int, int, Fraction, Iterator[np.ndarray]]:
+    """Luma planes through OpenCV's bundled libavcodec (software decode on the host, as in the reference).
+    decode_threads: libavcodec threads for this file (None = OpenCV's default, all cores)."""
     import cv2
-    cap = cv2.VideoCapture(path, cv2.CAP_FFMPEG)
+    if decode_threads is None:
+        cap = cv2.VideoCapture(path, cv2.CAP_FFMPEG)
+    else:
+        cap = cv2.VideoCapture(path, cv2.CAP_FFMPEG, [cv2.CAP_PROP_N_THREADS, int(decode_threads)])
     if not cap.isOpened():
         raise ValueError(f"cannot open {path!r}")
     if not cap.set(cv2.CAP_PROP_CONVERT_RGB, 0):
@@ -158,10 +162,86 @@ def cv2_frames(path: str) -> tuple[int, int, Fraction, Iterator[np.ndarray]]:
     return w, h, fps, it()
 
 
-def open_frames(path: str):
+def open_frames(path: str, decode_threads: int | None = None):
     with open(path, "rb") as f:
         magic = f.read(9)
-    return y4m_frames(path) if magic == b"YUV4MPEG2" else cv2_frames(path)
+    return y4m_frames(path) if magic == b"YUV4MPEG2" else cv2_frames(path, decode_threads)
+
+
+_PINNED: dict = {}                  # (chunk, h, w) -> idle pairs of pinned staging buffers
+_PINNED_LOCK = __import__("threading").Lock()
+
+
+def _pinned_pair(chunk: int, h: int, w: int):
+    import torch
+    with _PINNED_LOCK:
+        idle = _PINNED.setdefault((chunk, h, w), [])
+        if idle:
+            return idle.pop()
+    return [torch.empty((chunk, h, w), dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+
+def _release_pair(bufs) -> None:
+    key = tuple(bufs[0].shape)
+    with _PINNED_LOCK:
+        idle = _PINNED.setdefault(key, [])
+        if len(idle) < 64:
+            idle.append(bufs)
+
+
+def score_files(paths, threshold: float = 0.3, workers: int | None = None, chunk_frames: int = 32, fmt: str = "g6",
+                device: int | None = None) -> list[dict]:
+    """Several uploads at once, the way the reference runs one analysis thread per upload (app.py:43,472):
+    every worker thread decodes its file on the host (libavcodec releases the GIL), stages luma chunks in
+    its own pair of pinned buffers, copies them to the GPU on its own stream and scores them there
+    (``scene.StreamScorer``), so decode, PCIe and the SAD kernel of different uploads overlap.
+    -> [{cuts, frames, width, height}] in input order."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    import torch
+    paths = list(paths)
+    workers = max(1, min(len(paths), workers or len(os.sched_getaffinity(0))))
+    per_file = max(1, len(os.sched_getaffinity(0)) // workers)
+    dev = torch.cuda.current_device() if device is None else int(device)
+
+    def one(path):
+        w, h, fps, frames = open_frames(path, per_file)
+        time_base = (fps.denominator, fps.numerator)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.Stream()
+            bufs = _pinned_pair(chunk_frames, h, w)                # page-locking is slow: the pairs are recycled
+            views = [b.numpy() for b in bufs]
+            free = [torch.cuda.Event(), torch.cuda.Event()]       # buffer i has left for the device
+            scorer = scene.StreamScorer(threshold)
+            sels = []
+            b = k = total = 0
+
+            def ship(n):
+                nonlocal b
+                with torch.cuda.stream(stream):
+                    d = bufs[b][:n].to(torch.device("cuda", dev), non_blocking=True)
+                    free[b].record(stream)
+                    sels.append(scorer.feed(d)[2][0])
+                b ^= 1
+                free[b].synchronize()                              # (a never-recorded event is complete)
+
+            for frame in frames:
+                np.copyto(views[b][k], frame)
+                k += 1
+                if k == chunk_frames:
+                    ship(k)
+                    total, k = total + k, 0
+            if k:
+                ship(k)
+                total += k
+            stream.synchronize()
+            sel = torch.cat(sels).cpu().numpy() if sels else np.zeros(0, np.uint8)
+            _release_pair(bufs)
+        return {"cuts": scene.cut_timestamps(sel, None, time_base, fmt), "frames": total, "width": w, "height": h}
+
+    with ThreadPoolExecutor(workers) as pool:
+        return list(pool.map(one, paths))
 
 
 # ------------------------------------------------------------------ scoring + protocol

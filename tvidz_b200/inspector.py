@@ -11,6 +11,7 @@ Module-level functions act on a default `Inspector`, like db.py's module-level s
 from __future__ import annotations
 
 import threading
+import time
 from dataclasses import dataclass, field
 from typing import Iterable, Sequence
 
@@ -63,6 +64,7 @@ class Inspector:
         self._qlock = threading.Lock()              # the request queue
         self._pending: list[_Request] = []
         self._leader = False
+        self._crowd = 1
         self._videos: dict[int, Video] = {}
         self._rows: dict[int, list[float]] = {}     # video_id -> timestamps, ordered by last write
         self._next_id = 1
@@ -178,6 +180,13 @@ class Inspector:
             lead = req.promoted and req.result is None and req.error is None
         if lead:
             batch_size = 8
+            if self._crowd > 1:
+                # other threads have been asking concurrently: they are runnable but need the interpreter to
+                # queue their request -- yield to them (twice at most) before assembling the batch
+                for _ in range(2):
+                    time.sleep(0)
+                    if len(self._pending) >= self._crowd:
+                        break
             with self._qlock:
                 # the leader's own request first, then compatible ones in arrival order
                 self._pending.remove(req)
@@ -190,6 +199,7 @@ class Inspector:
                             batch.append(r)
                             self._pending.remove(r)
             self._run(batch)
+            self._crowd = max(len(batch), self._crowd - 1)          # how many callers shared recent passes (decays)
             with self._qlock:
                 nxt = self._pending[0] if self._pending else None
                 if nxt is None:
