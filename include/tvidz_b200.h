@@ -208,9 +208,10 @@ int tvz_catalog_match_batch_async(const tvz_catalog *cat, tvz_match_ws *ws, cons
                                   int64_t out_cap, void *stream);
 /* Sharded matcher with the gather fused into the kernel (one process per GPU, peers reachable
  * over NVLink): like tvz_catalog_match_async into the workspace's own record, but every CTA also
- * STORES its hits into every peer's gather buffer, the CTA that finishes last stores the header
- * {n_hits, overflow} and raises a per-rank flag there with a system-scope release, and then
- * waits (bounded) until the flags of all peers show `epoch` -- no second kernel, no collective.
+ * STORES its hits (and the last tile the header {n_hits, overflow}) into this rank's slot of every
+ * peer's gather buffer and fences them at system scope; the CTA that finishes last raises a
+ * per-rank flag on every peer and then waits (bounded) until the flags of all peers show `epoch`
+ * -- no second kernel, no collective.
  *   peer_record[p] : device address (peer memory) of THIS rank's slot, int32 [out_cap + 1][2],
  *                    inside peer p's gather buffer; peer_flag[p]: this rank's uint32 flag on peer p
  *   d_my_flags     : this rank's own flag array, uint32 [n_peers] (written by the peers)

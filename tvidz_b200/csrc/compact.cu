@@ -177,35 +177,45 @@ match_compact_kernel(int *__restrict__ counts, long long n_rows, int min_match, 
                 // per-row payload (fragment mode: best offset)
                 if (kKeys) aux_out[1 + pos] = dec[j];
                 else if (aux) aux_out[1 + pos] = aux[r0 + j];
-                // fused gather: every block ships its own hits to all peers (8-byte stores over NVLink);
-                // the per-row payload sits at the same distance behind the record as it does locally
-                for (int p = 0; p < gt.n_peers; ++p) {
-                    *reinterpret_cast<int2 *>(gt.record[p] + 2 + 2 * pos) = make_int2(vid[r0 + j], cnt[j]);
-                    if (aux_out) gt.record[p][(aux_out - out) + 1 + pos] = kKeys ? dec[j] : (aux ? aux[r0 + j] : 0);
-                }
             }
             ++pos;
         }
     }
     if (gt.n_peers == 0) return;
 
-    // ---- fused gather epilogue: the block that finishes last publishes the header and the flag ----
+    // ---- fused gather epilogue: the block that finishes last ships the finished record to every peer ----
+    // (one system-scope fence on the whole path, as in match_tile_kernel: header + hits, then the per-row
+    // payload, which sits at the same distance behind the record on the peers as it does locally)
     __shared__ unsigned s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();  // this block's peer stores (and the local header) before it counts as done
+        __threadfence();
         const unsigned done = atomicAdd(ticket + 2, 1u);
         s_last = done == gridDim.x - 1;
         if (s_last) ticket[2] = 0;
     }
     __syncthreads();
     if (!s_last) return;
+    __threadfence();
+    {
+        const int2 *src = reinterpret_cast<const int2 *>(out);
+        const long long n_hits = min(static_cast<long long>(__ldcg(out)), cap);
+        for (long long i = threadIdx.x; i < n_hits + 1; i += blockDim.x) {
+            const int2 v = __ldcg(src + i);
+            for (int p = 0; p < gt.n_peers; ++p) reinterpret_cast<int2 *>(gt.record[p])[i] = v;
+        }
+        if (aux_out) {
+            const long long rel = aux_out - out;
+            for (long long i = threadIdx.x; i < n_hits; i += blockDim.x) {
+                const int v = __ldcg(aux_out + 1 + i);
+                for (int p = 0; p < gt.n_peers; ++p) gt.record[p][rel + 1 + i] = v;
+            }
+        }
+    }
+    __syncthreads();
     if (threadIdx.x < gt.n_peers) {
         __threadfence_system();
-        const int2 hdr = make_int2(*reinterpret_cast<volatile int *>(out), *reinterpret_cast<volatile int *>(out + 1));
-        *reinterpret_cast<int2 *>(gt.record[threadIdx.x]) = hdr;  // {n_hits, overflow}
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gt.flag[threadIdx.x]), "r"(gt.epoch) : "memory");
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(gt.flag[threadIdx.x]), "r"(gt.epoch) : "memory");
     }
 }
 
@@ -215,9 +225,10 @@ __global__ void gather_wait_kernel(const unsigned *flags, int n_peers, unsigned 
     if (threadIdx.x >= n_peers) return;
     unsigned v, polls = 0;
     do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+        // (whatever reads the peers' records runs after this kernel: the poll needs no fence of its own)
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
         if (v == epoch) return;
-        __nanosleep(64);
+        if (polls > 256) __nanosleep(64);
     } while (++polls < (1u << 26));
     __trap();
 }

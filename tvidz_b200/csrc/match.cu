@@ -429,6 +429,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
     }
     __syncthreads();
     mark(9);
+    bool shipped = false;   // this thread stored something into a peer
     for (int b = 0; b < nq; ++b) {
         int cnt[S::kRowsPerThread];
         int mine = 0;
@@ -453,9 +454,10 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
                     const int2 hit = make_int2(a.vid[row], cnt[j]);
                     *reinterpret_cast<int2 *>(o + 2 + 2 * pos) = hit;
                     if (kQ == 1 && a.rows_out) a.rows_out[pos] = row;
-                    // fused gather: every CTA ships its own hits to all peers (8-byte stores over NVLink)
+                    // fused gather: every CTA ships its own hits to all peers (8-byte stores over NVLink), in parallel
                     for (int p = 0; p < a.gt.n_peers; ++p)
                         *reinterpret_cast<int2 *>(a.gt.record[p] + b * a.gt.query_stride + 2 + 2 * pos) = hit;
+                    shipped = a.gt.n_peers > 0;
                 }
                 ++pos;
             }
@@ -464,30 +466,39 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
     mark(10);
 
     // ---- fused gather: the CTA that finishes last raises this rank's flag on every peer ----
+    // A CTA that stored something into the peers fences it at system scope (one NVLink round trip,
+    // measured ~1.8 us; the CTAs do it in parallel, and most tiles of a selective query ship nothing and
+    // skip it) before it counts itself done; the last one fences once more and raises the flags, then
+    // waits (bounded) until the flags of all peers show this query.
     if (a.gt.n_peers == 0) return;   // (the query sequence number comes from the host: nothing to re-arm)
-    __syncthreads();
+    const int any_shipped = __syncthreads_or(shipped || (tile == a.n_tiles - 1 && tid < nq));   // (the header is peer traffic too)
     mark(11);
     if (warp != 0) return;
     unsigned last = 0;
     if (lane == 0) {
-        __threadfence_system();  // this CTA's peer stores before it counts as done
+        if (any_shipped) __threadfence_system();
+        else __threadfence();
         last = atomicAdd(a.ctrl, 1u) == gridDim.x - 1;
         if (last) a.ctrl[0] = 0;
     }
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
+    mark(12);
     if (lane < a.gt.n_peers) {
-        // every CTA fenced its peer stores at system scope before it counted as done, and this warp has
-        // seen all of them count: the release below makes the whole record visible before the flag
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.gt.flag[lane]), "r"(a.gt.epoch) : "memory");
-        // ... and wait until every peer's record for this epoch has landed here (bounded, see above)
+        __threadfence_system();   // every CTA's peer stores happen before its count, the counts before this fence
+        mark(13);
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.gt.flag[lane]), "r"(a.gt.epoch) : "memory");
+        mark(14);
+        // The peers' records are in this GPU's memory once their flags are: whatever reads them runs after this
+        // kernel has completed, so the poll needs no fence of its own.
         unsigned f, polls = 0;
         do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(a.my_flags + lane) : "memory");
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(a.my_flags + lane) : "memory");
             if (f == a.gt.epoch) break;
-            __nanosleep(64);
-            if (++polls == (1u << 26)) __trap();
+            if (++polls > 256) __nanosleep(64);
+            if (polls == (1u << 26)) __trap();
         } while (true);
+        mark(15);
     }
 }
 
