@@ -24,3 +24,13 @@ if what in ("match", "both"):
         cat.match_async(q, 2, rec)
     torch.cuda.synchronize()
     print("hits", int(rec[0, 0]))
+if what == "batch":
+    import numpy as np
+    ts, off, vid = synth.synth_catalogue(1_000_000, seed=0)
+    cat = Catalogue(ts, off, vid, hit_capacity=1 << 15)
+    qs = [ts[off[r]:off[r + 1]].copy() for r in np.random.default_rng(7).integers(0, 1_000_000, 8)]
+    rec8 = torch.zeros((8, (1 << 15) + 1, 2), dtype=torch.int32, device=dev)
+    for _ in range(reps):
+        cat.match_batch_async(qs, 2, rec8)
+    torch.cuda.synchronize()
+    print("hits", rec8[:, 0, 0].tolist())

@@ -154,6 +154,30 @@ def test_full_size_properties(cuda):
         assert np.array_equal(sad[s:s + 1].cpu().numpy().astype(np.uint64), o_sad)
 
 
+@pytest.mark.parametrize("chunks", [[1, 1, 10], [5, 7], [12]])
+def test_stream_scorer_ten_bit_chunks(cuda, chunks):
+    """16-bit samples fed chunk by chunk: the carried frame keeps its 16 bits and mafd is divided by
+    2^(bitdepth-8) for the carry pair as for the chunk -- identical to one call and to the oracle; the
+    P016 layout NVDEC writes (sample in the HIGH bits) scores the same with bitdepth = 16."""
+    rng = np.random.default_rng(sum(chunks))
+    f = rng.integers(0, 1024, (2, 12, 40, 64), dtype=np.uint16)
+    f[:, 5:] = np.clip(f[:, 5:].astype(np.int32) + 300, 0, 1023).astype(np.uint16)          # a cut at frame 5
+    o_sad, o_score, o_sel, _ = oracle.scene_batch(f, bitdepth=10)
+    for shift, depth in ((0, 10), (6, 16)):
+        d = torch.from_numpy((f << shift).view(np.int16)).to(cuda)
+        sc = scene.StreamScorer(bitdepth=depth)
+        got, t = [], 0
+        for n in chunks:
+            got.append(sc.feed(d[:, t:t + n]))
+            t += n
+        sad = torch.cat([g[0] for g in got], 1).cpu().numpy().astype(np.uint64)
+        assert np.array_equal(sad, o_sad << np.uint64(shift))
+        assert np.array_equal(torch.cat([g[1] for g in got], 1).cpu().numpy(), o_score)
+        assert np.array_equal(torch.cat([g[2] for g in got], 1).cpu().numpy(), o_sel) and o_sel[:, 5].all()
+    with pytest.raises((TypeError, ValueError)):
+        scene.StreamScorer(bitdepth=8).feed(torch.from_numpy(f.view(np.int16)).to(cuda))
+
+
 @pytest.mark.parametrize("chunks", [[1, 1, 1, 37], [16, 16, 8], [40], [7, 0, 33], [39, 1]])
 def test_stream_scorer_equals_one_shot(cuda, chunks):
     """Long-form video fed chunk by chunk (BASELINE config 3 shape: 4K frames) == one call."""

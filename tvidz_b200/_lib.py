@@ -62,6 +62,7 @@ SYMBOLS = [
 ]
 # debug hooks outside the public header
 _DEBUG_SYMBOLS = [("tvz_debug_sad_tuning", _i, [_i, _i, _i, _i]),
+                  ("tvz_debug_flush_l2", _i, [_vp, _i64, _vp]),
                   ("tvz_debug_match_timing", _i, [_vp, _i]),
                   ("tvz_debug_match_count_ms", _i, [_vp, C.POINTER(C.c_float)]),
                   ("tvz_debug_tile_trace", _i, [_vp, _vp]),

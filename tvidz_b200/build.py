@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["common.cu", "sad.cu", "scene_host.cu", "compact.cu", "match.cu", "fragment.cu", "nvdec.cu"]
-OUT = os.path.join(HERE, "libtvidz_b200.so")
+OUT = os.environ.get("TVZ_BUILD_OUT") or os.path.join(HERE, "libtvidz_b200.so")   # (checked / tuning variants go elsewhere)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-ldl"]

@@ -157,10 +157,27 @@ struct TileArgs {
     int uniform_units;                      // > 0: packed tile t starts at unit t * uniform_units (no lookup before the first loads)
     const unsigned *my_flags;               // fused gather: this rank's flags, written by the peers
     long long *trace;                       // debug: [n_tiles][16] phase timestamps (tvz_debug_tile_trace), normally null
+    long long n_pos, n_rows_cap;            // checked build: arranged positions / rows the arrays hold
     GatherTargets gt;
 };
 
 // L2-coherent accesses to the words CTAs exchange (no L1, no fence of their own)
+// Checked build (-DTVZ_CHECKED, scripts/checked_build.sh): every index the tile and upsert kernels compute is
+// tested against its bound and a violation traps with a message -- this pool's GPUs refuse compute-sanitizer
+// (profiles/r02_sanitizer_refused.txt), so the bounds checks are the library's own.
+#ifdef TVZ_CHECKED
+#define TVZ_CHECK(cond)                                                                                     \
+    do {                                                                                                    \
+        if (!(cond)) {                                                                                      \
+            printf("tvidz_b200 CHECK failed: %s (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__,  \
+                   (int)blockIdx.x, (int)threadIdx.x);                                                      \
+            __trap();                                                                                       \
+        }                                                                                                   \
+    } while (0)
+#else
+#define TVZ_CHECK(cond) ((void)0)
+#endif
+
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -226,6 +243,10 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
     for (int i = tid; i < S::kCountWords / 4; i += S::kThreads)
         reinterpret_cast<uint4 *>(sm.counts)[i] = make_uint4(0u, 0u, 0u, 0u);
     const unsigned unit_hi = scan ? td.unit_hi : unit_lo;
+    TVZ_CHECK(td.n_rows >= 0 && td.n_rows <= kTileRows && td.row_lo >= 0 && td.row_lo + td.n_rows <= a.n_rows_cap);
+    TVZ_CHECK(td.unit_hi >= td.unit_lo && static_cast<long long>(td.unit_hi) * kFpPerUnit <= a.n_pos);
+    TVZ_CHECK(!uniform || td.unit_lo == unit_lo);
+    TVZ_CHECK(tile < a.n_tiles && (kQ > 1 || a.n_keys >= 0));
     if (!uniform) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -268,6 +289,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
     // ---- stream the tile's fingerprints; survivors are parked per warp and verified at the end ----
     const long long pos0 = static_cast<long long>(unit_lo) * kFpPerUnit;
     auto resolve = [&](unsigned rel) {
+        TVZ_CHECK(pos0 + rel < a.n_pos && pos0 + rel < static_cast<long long>(unit_hi) * kFpPerUnit);
         const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(a.rec + pos0 + rel));
         const unsigned long long val = (static_cast<unsigned long long>(r4.y) << 32) | r4.x;
         const unsigned local = r4.z - static_cast<unsigned>(td.row_lo);
@@ -283,6 +305,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
                 if (lo >= a.n_keys || __ldg(a.keys_g + lo) != val) return;
                 m = __ldg(a.mult_g + lo);
             }
+            TVZ_CHECK(local < static_cast<unsigned>(kTileRows));
             atomicAdd(&sm.counts[local], static_cast<unsigned>(m));
         } else {
             unsigned qm = sm.map[filter_hash(val)];
@@ -292,6 +315,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
                 const int nk = sm.n_keys[b];
                 const int lo = lower_bound_u64([&](int i) { return sm.keys[b][i]; }, nk, val);
                 if (lo >= nk || sm.keys[b][lo] != val) continue;       // filter false positive for this query
+                TVZ_CHECK(b < kQ && local < static_cast<unsigned>(kTileRows));
                 atomicAdd(&sm.counts[b * (kTileRows / 2) + (local >> 1)],
                           static_cast<unsigned>(sm.mult[b][lo]) << (16 * (local & 1)));
             }
@@ -331,6 +355,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
                     if (queued + __popc(mask) > S::kQueue) drain();
                     if (flags) {
                         const unsigned e = e0 + (__ffs(flags) - 1);
+                        TVZ_CHECK(queued + __popc(mask & ((1u << lane) - 1u)) < S::kQueue);
                         qe[queued + __popc(mask & ((1u << lane) - 1u))] = e;
                         flags &= flags - 1;
                         // what the verification will read, on its way to L2 while the stream goes on
@@ -449,8 +474,10 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
 #pragma unroll
         for (int j = 0; j < S::kRowsPerThread; ++j) {
             if (cnt[j] >= 0) {
+                TVZ_CHECK(pos >= 0);
                 if (pos < a.cap) {
                     const int row = td.row_lo + r0 + j;
+                    TVZ_CHECK(row < a.n_rows_cap && r0 + j < td.n_rows);
                     const int2 hit = make_int2(a.vid[row], cnt[j]);
                     *reinterpret_cast<int2 *>(o + 2 + 2 * pos) = hit;
                     if (kQ == 1 && a.rows_out) a.rows_out[pos] = row;
@@ -543,11 +570,14 @@ struct UpsertArgs {
     long long kill_pos_lo, kill_pos_hi;    // arranged positions that may hold the replaced row's records
     long long kill_ts_lo, kill_ts_hi;      // its values in row order
     long long new_row, pos0, ts0;          // where the new row goes: arranged position (tail: identity order) and row-order position
+    long long n_pos, n_ts, n_rows_cap;     // checked build: what the arrays hold
     int new_vid, n;
     const unsigned long long *vals_g;      // n > kParamKeys: values staged in device memory
     unsigned long long vals[kParamKeys];
 };
 __global__ void __launch_bounds__(512) upsert_kernel(const __grid_constant__ UpsertArgs u) {
+    TVZ_CHECK(u.n >= 0 && u.pos0 >= 0 && u.pos0 + u.n <= u.n_pos && u.ts0 + u.n <= u.n_ts && u.new_row >= 0 && u.new_row < u.n_rows_cap);
+    TVZ_CHECK(u.kill_row < u.n_rows_cap && (u.kill_row < 0 || (u.kill_pos_lo >= 0 && u.kill_pos_hi <= u.n_pos && u.kill_ts_hi <= u.n_ts)));
     if (u.kill_row >= 0) {
         for (long long p = u.kill_pos_lo + threadIdx.x; p < u.kill_pos_hi; p += blockDim.x)
             if (u.rec[p].row == static_cast<unsigned>(u.kill_row)) u.rec[p].ts = kPadPattern;
@@ -600,6 +630,7 @@ struct tvz_catalog {
     TileDesc *d_tiles = nullptr;
     std::vector<TileDesc> tiles;             // tiles of the packed rows
     int uniform_units = 0;                   // > 0: packed tile t starts at unit t * uniform_units
+    long long n_pos_all = 0, n_ts_all = 0, rows_cap = 0;   // what the device arrays hold (checked build)
     int tail_index = -1;
     // ---- mutable tail (tvz_catalog_upsert); everything below is guarded by `mu` ----
     mutable std::mutex mu;
@@ -900,6 +931,8 @@ void base_args(const tvz_catalog *cat, tvz_match_ws *ws, const CatView &cv, Tile
     a.ctrl = ws->d_ctrl;
     a.n_hits_out = ws->d_nhits;
     a.uniform_units = cat->uniform_units;
+    a.n_pos = cat->n_pos_all;
+    a.n_rows_cap = cat->rows_cap;
     a.trace = ws->d_trace;
     ws->seq = ws->seq >= 0xffffu ? 1u : ws->seq + 1u;   // never 0: that is what fresh state[] entries carry
     a.seq = ws->seq;
@@ -1219,6 +1252,9 @@ int catalog_create(const double *h_ts, const int64_t *h_off, const int32_t *h_vi
     const size_t n_pos_all = static_cast<size_t>(std::max<long long>(1, n_units_all)) * kFpPerUnit;
     const size_t n_fp_alloc = n_pos_all + static_cast<size_t>(kFpPadUnits) * kFpPerUnit;
     const size_t n_ts_all = static_cast<size_t>(std::max<long long>(1, c->ts_main_padded + c->tail_cap_vals));
+    c->n_pos_all = static_cast<long long>(n_pos_all);
+    c->n_ts_all = static_cast<long long>(n_ts_all);
+    c->rows_cap = rows_cap;
     if ((e = cudaMalloc(&c->d_fp, n_fp_alloc * 2)) != cudaSuccess) return fail(e, "cudaMalloc(fp)");
     if ((e = cudaMemset(c->d_fp, 0, n_fp_alloc * 2)) != cudaSuccess) return fail(e, "cudaMemset(fp)");
     if ((e = cudaMalloc(&c->d_rec, n_pos_all * sizeof(VerifyRec))) != cudaSuccess) return fail(e, "cudaMalloc(rec)");
@@ -1447,6 +1483,9 @@ int tvz_catalog_upsert(tvz_catalog *c, int32_t video_id, const double *h_ts, int
     u.ts0 = c->ts_main_padded + start;
     u.new_vid = video_id;
     u.n = nv;
+    u.n_pos = c->n_pos_all;
+    u.n_ts = c->n_ts_all;
+    u.n_rows_cap = c->rows_cap;
     if (nv <= kParamKeys) {
         memcpy(u.vals, vals.data(), sizeof(unsigned long long) * nv);
     } else {
