@@ -160,8 +160,10 @@ def test_stream_scorer_ten_bit_chunks(cuda, chunks):
     2^(bitdepth-8) for the carry pair as for the chunk -- identical to one call and to the oracle; the
     P016 layout NVDEC writes (sample in the HIGH bits) scores the same with bitdepth = 16."""
     rng = np.random.default_rng(sum(chunks))
-    f = rng.integers(0, 1024, (2, 12, 40, 64), dtype=np.uint16)
-    f[:, 5:] = np.clip(f[:, 5:].astype(np.int32) + 300, 0, 1023).astype(np.uint16)          # a cut at frame 5
+    base = rng.integers(100, 600, (2, 1, 40, 64))
+    f = base + rng.integers(0, 8, (2, 12, 40, 64))                                          # one scene, small noise ...
+    f[:, 5:] += 300                                                                          # ... and a cut at frame 5
+    f = f.astype(np.uint16)
     o_sad, o_score, o_sel, _ = oracle.scene_batch(f, bitdepth=10)
     for shift, depth in ((0, 10), (6, 16)):
         d = torch.from_numpy((f << shift).view(np.int16)).to(cuda)

@@ -187,6 +187,23 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned *p, unsigned v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Start the fetch of a survivor's verification record without waiting for it.  TVZ_WARM: 1 = prefetch.global.L2
+// (brings the whole 128-byte line, or more), 2 = a 4-byte load whose result is never used (brings the sector),
+// 0 = nothing (the verification pays the full latency).
+#ifndef TVZ_WARM
+#define TVZ_WARM 2
+#endif
+__device__ __forceinline__ void warm_record(const void *p) {
+#if TVZ_WARM == 1
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#elif TVZ_WARM == 2
+    unsigned unused;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(unused) : "l"(p));
+#else
+    (void)p;
+#endif
+}
+
 template <class T>
 __device__ __forceinline__ int lower_bound_u64(const T &at, int n, unsigned long long v) {
     int lo = 0, hi = n;
@@ -359,7 +376,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
                         qe[queued + __popc(mask & ((1u << lane) - 1u))] = e;
                         flags &= flags - 1;
                         // what the verification will read, on its way to L2 while the stream goes on
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rec + pos0 + e));
+                        warm_record(a.rec + pos0 + e);
                     }
                     queued += __popc(mask);
                     mask = __ballot_sync(0xffffffffu, flags != 0u);
