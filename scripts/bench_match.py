@@ -51,6 +51,23 @@ for n in sizes:
         cat.match_async(q, 2, rec)
         ks.append(cat.debug_count_kernel_ms() * 1e3)
     cat.debug_count_kernel_ms(False)
+    # a selective query (the reference's default min_match = 5): most tiles have no hit and skip the exchange
+    for _ in range(3):
+        cat.match_async(q, 5, rec)
+    e0.record(stream)
+    for _ in range(K):
+        cat.match_async(q, 5, rec)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    mm5_b2b = e0.elapsed_time(e1) / K * 1e3
+    for a, b in evs:
+        flush.zero_()
+        sink += flush.view(torch.int64).sum()
+        a.record(stream)
+        cat.match_async(q, 5, rec)
+        b.record(stream)
+    torch.cuda.synchronize()
+    mm5_cold = float(np.mean([a.elapsed_time(b) for a, b in evs])) * 1e3
     # the fixed cost alone: an empty query runs the same kernel without streaming anything
     qe = np.zeros(0)
     for _ in range(3):
@@ -91,6 +108,6 @@ for n in sizes:
         full5 = cat.find_duplicates(q, 5)
     e2e5 = (time.perf_counter() - t0) / 50 * 1e6
     print(f"rows {n:>8} tiles {cat.n_tiles:>4} values {cat.n_values:>9}: b2b {b2b:6.1f} us  cold {cold:6.1f} us  kernel(cold) {np.mean(ks):6.1f} us  "
-          f"host enqueue {host_us:5.1f} us  floor(empty query) b2b {floor_b2b:5.1f} cold {floor_cold:5.1f} us | batch8 pass {b8:6.1f} us ({b8 / 8:5.1f}/query) host {host8_us:5.1f} us | "
+          f"mm5 b2b {mm5_b2b:5.1f} cold {mm5_cold:5.1f} us  host enqueue {host_us:5.1f} us  floor(empty query) b2b {floor_b2b:5.1f} cold {floor_cold:5.1f} us | batch8 pass {b8:6.1f} us ({b8 / 8:5.1f}/query) host {host8_us:5.1f} us | "
           f"e2e mm2 {e2e:6.1f} us ({len(full)} hits) mm5 {e2e5:6.1f} us ({len(full5)} hits)", flush=True)
     cat.close()

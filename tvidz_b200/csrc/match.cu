@@ -183,6 +183,20 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// How a predecessor's total is polled.  TVZ_POLL_LD: 0 = ld.relaxed.gpu (a strong load per lane), 1 = ld.global.cg
+// (L2-only weak load, volatile asm so that the loop re-reads; the warp's lanes coalesce into line requests)
+#ifndef TVZ_POLL_LD
+#define TVZ_POLL_LD 0   // measured: no difference (125k-row shard, cold 23.4 vs 24.5 us, back to back 14.7 both)
+#endif
+__device__ __forceinline__ unsigned ld_poll_u32(const unsigned *p) {
+#if TVZ_POLL_LD == 0
+    return ld_relaxed_u32(p);
+#else
+    unsigned v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
 __device__ __forceinline__ void st_relaxed_u32(unsigned *p, unsigned v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -191,7 +205,7 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned *p, unsigned v) {
 // (brings the whole 128-byte line, or more), 2 = a 4-byte load whose result is never used (brings the sector),
 // 0 = nothing (the verification pays the full latency).
 #ifndef TVZ_WARM
-#define TVZ_WARM 2
+#define TVZ_WARM 1   // measured (profiles/r02_warm_variants.txt): same DRAM bytes for all three, 1 and 2 are ~2 us faster than 0
 #endif
 __device__ __forceinline__ void warm_record(const void *p) {
 #if TVZ_WARM == 1
@@ -433,17 +447,23 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
         }
     }
     mark(7);
-    {   // hits of all earlier tiles
+    // A tile without a single qualifying row (most tiles of a selective query) has nothing to place: it
+    // needs no offset, polls nothing and is done -- only the last tile always goes on (it writes the header).
+    __syncthreads();
+    bool shipped = false;   // this thread stored something into a peer
+    bool idle = tile != a.n_tiles - 1;
+    for (int b = 0; b < nq; ++b) idle = idle && sm.agg[b] == 0;
+    if (!idle) {   // hits of all earlier tiles
         const unsigned seq = a.seq;
         const int b = tid / S::kGroup, i0 = tid - b * S::kGroup;
         unsigned long long sum = 0;
         if (b < nq) {
             for (int i = i0; i < tile; i += S::kGroup) {
                 const unsigned *p = &a.state[static_cast<size_t>(i) * kQ + b];
-                unsigned r = ld_relaxed_u32(p), polls = 0;
+                unsigned r = ld_poll_u32(p), polls = 0;
                 while ((r >> 16) != seq) {   // bounded: a protocol bug must surface as a launch failure, never as a hung GPU
                     if (++polls == (1u << 24)) __trap();
-                    r = ld_relaxed_u32(p);
+                    r = ld_poll_u32(p);
                 }
                 sum += r & 0xffffu;
             }
@@ -451,7 +471,6 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (lane == 0) sm.part[warp] = sum;
-    }
     __syncthreads();
     mark(8);
     if (tid < nq) {
@@ -471,7 +490,6 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
     }
     __syncthreads();
     mark(9);
-    bool shipped = false;   // this thread stored something into a peer
     for (int b = 0; b < nq; ++b) {
         int cnt[S::kRowsPerThread];
         int mine = 0;
@@ -507,6 +525,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
             }
         }
     }
+    }   // !idle
     mark(10);
 
     // ---- fused gather: the CTA that finishes last raises this rank's flag on every peer ----

@@ -214,12 +214,16 @@ class ShardedCatalogue:
         while True:
             g = self.enqueue(new_timestamps, min_match)
             heads = self._read(g, self._host, self._host_np, self.world, self.rec_ints)
-            n_max = int(heads[:, 0].max()) if heads.size else 0
-            if heads[:, 1].any() or n_max > self.cap:
+            hl = heads.tolist()                                   # [[n_hits, overflow], ...]: plain ints from here on
+            n_max = max(h[0] for h in hl) if hl else 0
+            if n_max > self.cap or any(h[1] for h in hl):
                 self._regrow(n_max)
                 continue
-            pairs, _, _ = merge_records(self._host_np[:, :n_max + 1, :], self.cap)
-            flat = pairs.reshape(-1).tolist()                     # one tolist() for the whole result
+            flat: list = []
+            host = self._host_np
+            for r, (n, _) in enumerate(hl):                       # shards in rank order = catalogue order
+                if n:
+                    flat += host[r, 1:1 + n].ravel().tolist()
             return list(zip(flat[0::2], flat[1::2]))
 
     # ---- 8 queries per pass --------------------------------------------------------------
