@@ -497,7 +497,8 @@ def run_ours(args):
             full = lambda m=mm: cat.find_duplicates(q, m)                        # noqa: E731
             local_cat = cat
         else:
-            sc = ShardedCatalogue(ts, off, vid, hit_capacity=cap, device=local, gather=args.gather)
+            sc = ShardedCatalogue(ts, off, vid, hit_capacity=cap, device=local, gather=args.gather,
+                                  multicast=not args.no_multicast)
             enqueue = lambda: sc.enqueue(q, mm)                                  # noqa: E731
             full = lambda m=mm: sc.find_duplicates(q, m)                         # noqa: E731
             local_cat = sc.local
@@ -635,8 +636,10 @@ def run_ours(args):
                                "min_match": mm, "hits": len(hits),
                                "collective": "none" if world == 1 else (
                                    "fused: the query's kernel stores each shard's hit record into every peer over NVLink "
-                                   "(symmetric memory), raises a flag and waits for the peers' flags; no NCCL call on the "
-                                   "data path" if args.gather == "fused" else
+                                   "(symmetric memory" + (", through the NVSwitch multicast mapping" if getattr(sc._sym, "multicast", 0) else
+                                                          ", one store per peer") +
+                                   ") as epoch-tagged 8-byte words and its last CTAs wait until all peers' records are "
+                                   "complete; no fence, flag or NCCL call on the data path" if args.gather == "fused" else
                                    f"NCCL all_gather of int32 [{cap + 1},2] per-shard hit records"),
                                "catalogue_exceeds_l2": bool(2 * n_values > 126e6)},
                     "e2e": {"value": CATALOGUE_ROWS / (m_e2e * 1e-3), "unit": "pairs/s", "ms_per_query": m_e2e,
@@ -675,7 +678,7 @@ def run_ours(args):
             wts, woff, wvid = synth.synth_catalogue(CATALOGUE_ROWS, seed=1000 + rank)
             wvid = (wvid.astype(np.int64) + rank * CATALOGUE_ROWS).astype(np.int32)
             wsc = ShardedCatalogue(wts, woff, wvid, hit_capacity=1 << 15, device=local, gather=args.gather,
-                                   presharded=True)
+                                   presharded=True, multicast=not args.no_multicast)
             w_hits = wsc.find_duplicates(q, mm)
             mine = [h for h in w_hits if rank * CATALOGUE_ROWS < h[0] <= (rank + 1) * CATALOGUE_ROWS]
             ok_weak = mine == oracle.find_duplicates_csr(wts, woff, wvid, q, mm)      # this rank's slice of the full list
@@ -896,6 +899,7 @@ def main():
     ap.add_argument("--no-weak", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--no-from-file", action="store_true")
+    ap.add_argument("--no-multicast", action="store_true", help="fused gather: one store per peer instead of the multicast mapping")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="how the sharded matcher exchanges per-shard hit records at N > 1")
     args = ap.parse_args()

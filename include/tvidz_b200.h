@@ -208,24 +208,29 @@ int tvz_catalog_match_batch_async(const tvz_catalog *cat, tvz_match_ws *ws, cons
                                   int64_t out_cap, void *stream);
 /* Sharded matcher with the gather fused into the kernel (one process per GPU, peers reachable
  * over NVLink): like tvz_catalog_match_async into the workspace's own record, but every CTA also
- * STORES its hits (and the last tile the header {n_hits, overflow}) into this rank's slot of every
- * peer's gather buffer and fences them at system scope; the CTA that finishes last raises a
- * per-rank flag on every peer and then waits (bounded) until the flags of all peers show `epoch`
- * -- no second kernel, no collective.
- *   peer_record[p] : device address (peer memory) of THIS rank's slot, int32 [out_cap + 1][2],
- *                    inside peer p's gather buffer; peer_flag[p]: this rank's uint32 flag on peer p
- *   d_my_flags     : this rank's own flag array, uint32 [n_peers] (written by the peers)
- * Use a different buffer set for consecutive epochs (double buffering): a peer may start
- * query k+1 while this rank still reads the records of query k.  n_peers <= 8. */
+ * STORES its hits (and the last tile the header) into this rank's slot of every peer's gather
+ * buffer, in a TAGGED form: entry e of a slot is 16 bytes {value0, epoch, value1, epoch} -- entry 0 =
+ * {n_hits, overflow}, entry 1 + h = {video_id, match_count} -- and every 8-byte half is stored
+ * atomically, so a reader that finds `epoch` in both halves has the data.  Senders need no
+ * system-scope fence, no flag and no counter; the kernel's last CTA polls (bounded) the slots of all
+ * peers in this rank's OWN buffer until they are complete for `epoch` -- no second kernel, no
+ * collective.  When the kernel has completed, every shard's record is in d_my_slots.
+ *   peer_record[p] : device address (peer memory) of THIS rank's slot inside peer p's buffer;
+ *                    a slot holds 4 * (out_cap + 1) ints (x 8 for the batched form), 16-byte aligned.
+ *                    n_dst = n_peers such addresses, or n_dst = 1: ONE multicast address of the slot
+ *                    (NVSwitch replicates every store to all peers: 1/n_peers of the store instructions)
+ *   d_my_slots     : this rank's own buffer: n_peers slots, slot_stride_ints apart (slot p is written by peer p)
+ * Use a different buffer set for consecutive epochs (double buffering): a peer may start query k+1
+ * while this rank still reads the records of query k.  Buffers start zeroed; epoch != 0.  n_peers <= 8. */
 int tvz_catalog_match_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn,
-                                   int min_match, int n_peers, const uint64_t *peer_record,
-                                   const uint64_t *peer_flag, const uint32_t *d_my_flags, int64_t out_cap,
+                                   int min_match, int n_peers, int n_dst, const uint64_t *peer_record,
+                                   const int32_t *d_my_slots, int64_t slot_stride_ints, int64_t out_cap,
                                    uint32_t epoch, void *stream);
-/* The batched form: this rank's slot on every peer is int32 [8][out_cap + 1][2]. */
+/* The batched form: a slot is int32 [8][out_cap + 1][4]. */
 int tvz_catalog_match_batch_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
-                                         const int64_t *q_off, int n_queries, int min_match, int n_peers,
-                                         const uint64_t *peer_record, const uint64_t *peer_flag,
-                                         const uint32_t *d_my_flags, int64_t out_cap, uint32_t epoch,
+                                         const int64_t *q_off, int n_queries, int min_match, int n_peers, int n_dst,
+                                         const uint64_t *peer_record, const int32_t *d_my_slots,
+                                         int64_t slot_stride_ints, int64_t out_cap, uint32_t epoch,
                                          void *stream);
 /* Strided device -> host copy of a slice of n fixed-size records: bytes [offset, offset + width) of
  * every record, pitch_bytes apart on the device and in h_rec alike; sync != 0 waits for the stream.

@@ -46,8 +46,8 @@ SYMBOLS = [
                                      C.POINTER(_i64)]),
     ("tvz_catalog_match_async", _i, [_vp, _vp, _vp, _i, _i, _vp, _i64, _vp]),
     ("tvz_catalog_match_batch_async", _i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i64, _vp]),
-    ("tvz_catalog_match_gather_async", _i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64, C.c_uint32, _vp]),
-    ("tvz_catalog_match_batch_gather_async", _i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64, C.c_uint32,
+    ("tvz_catalog_match_gather_async", _i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i64, _i64, C.c_uint32, _vp]),
+    ("tvz_catalog_match_batch_gather_async", _i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i64, _i64, C.c_uint32,
                                                   _vp]),
     ("tvz_copy_records_to_host", _i, [_vp, _vp, _i, _i64, _i64, _i64, _i, _vp]),
     ("tvz_match_ws_hits", _vp, [_vp]),

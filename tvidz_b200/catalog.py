@@ -283,28 +283,29 @@ class Catalogue:
                                                       len(queries), int(min_match), out.data_ptr(), cap,
                                                       self._stream(stream)))
 
-    def match_gather_async(self, new_timestamps, min_match: int, peer_record: np.ndarray, peer_flag: np.ndarray,
-                           my_flags_ptr: int, out_cap: int, epoch: int, stream=None) -> None:
-        """Enqueue one query whose per-shard record is stored straight into every peer's gather
-        buffer by the query's kernel, which then waits for the peers' flags
-        (tvz_catalog_match_gather_async).  peer_record / peer_flag: contiguous uint64 arrays."""
+    def match_gather_async(self, new_timestamps, min_match: int, n_peers: int, peer_record: np.ndarray, my_slots_ptr: int,
+                           slot_stride_ints: int, out_cap: int, epoch: int, stream=None) -> None:
+        """Enqueue one query whose per-shard record is stored straight into every peer's gather buffer (tagged
+        entries) by the query's kernel, whose last CTA waits until all peers' records have landed here
+        (tvz_catalog_match_gather_async).  peer_record: contiguous uint64 array of n_peers peer addresses, or of ONE
+        multicast address that reaches all peers."""
         q = _as_query(new_timestamps)
         ws = self._ws_async(out_cap)
         with torch.cuda.device(self.device):
             check(lib().tvz_catalog_match_gather_async(self._handle, ws.handle, q.ctypes.data, q.shape[0], int(min_match),
-                                                       int(peer_record.shape[0]), peer_record.ctypes.data,
-                                                       peer_flag.ctypes.data, int(my_flags_ptr), int(out_cap),
+                                                       int(n_peers), int(peer_record.shape[0]), peer_record.ctypes.data,
+                                                       int(my_slots_ptr), int(slot_stride_ints), int(out_cap),
                                                        int(epoch) & 0xffffffff, self._stream(stream)))
 
-    def match_batch_gather_async(self, queries, min_match: int, peer_record: np.ndarray, peer_flag: np.ndarray,
-                                 my_flags_ptr: int, out_cap: int, epoch: int, stream=None) -> None:
-        """The batched form of match_gather_async: this rank's slot on every peer is [8, out_cap + 1, 2]."""
+    def match_batch_gather_async(self, queries, min_match: int, n_peers: int, peer_record: np.ndarray, my_slots_ptr: int,
+                                 slot_stride_ints: int, out_cap: int, epoch: int, stream=None) -> None:
+        """The batched form of match_gather_async: a slot is [8, out_cap + 1, 4]."""
         q_all, q_off = self._pack_queries(queries)
         ws = self._ws_async(out_cap)
         with torch.cuda.device(self.device):
             check(lib().tvz_catalog_match_batch_gather_async(
                 self._handle, ws.handle, q_all.ctypes.data, q_off.ctypes.data, len(queries), int(min_match),
-                int(peer_record.shape[0]), peer_record.ctypes.data, peer_flag.ctypes.data, int(my_flags_ptr),
+                int(n_peers), int(peer_record.shape[0]), peer_record.ctypes.data, int(my_slots_ptr), int(slot_stride_ints),
                 int(out_cap), int(epoch) & 0xffffffff, self._stream(stream)))
 
     def debug_count_kernel_ms(self, enable: bool | None = None) -> float | None:

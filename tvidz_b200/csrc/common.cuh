@@ -20,10 +20,15 @@ int num_sms();                          // SM count of the current device (cache
 constexpr int kMaxPeers = 8;
 struct GatherTargets {
     int n_peers = 0;                 // 0 = no gather
+    int n_dst = 0;                   // addresses in record[]: n_peers (one per peer), or 1 = a multicast address (NVSwitch replicates)
     unsigned epoch = 0;
     long long query_stride = 0;      // batched queries: ints between the records of consecutive queries
     int *record[kMaxPeers] = {};     // this rank's slot inside peer p's gather buffer (peer memory)
-    unsigned *flag[kMaxPeers] = {};  // this rank's flag word on peer p
+    unsigned *flag[kMaxPeers] = {};  // this rank's flag word on peer p (flag protocol: fragment compaction)
+    // tagged protocol (match_tile_kernel): every 8-byte word of a record carries the query epoch, so a record is
+    // complete when all its words show it -- no fence, no flag, no counter on the sender's side
+    const int *my_slots = nullptr;   // this rank's own gather buffer: n_peers slots, slot_stride ints apart
+    long long slot_stride = 0;
 };
 
 // compact.cu: single-pass ordered compaction of per-row results (fragment mode).

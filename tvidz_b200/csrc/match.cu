@@ -105,15 +105,22 @@ struct alignas(16) TileDesc {
     unsigned unit_lo, unit_hi;
 };
 
+// TVZ_Q1_WIDE = 1: the single-query kernel runs ONE 1024-thread CTA per SM on a PAIR of adjacent tiles (half the
+// CTAs in the tile-total exchange, one byte map per SM to zero instead of two); 0: one 512-thread CTA per tile, 2 per SM.
+#ifndef TVZ_Q1_WIDE
+#define TVZ_Q1_WIDE 0
+#endif
 template <int kQ>
 struct TileShape {
-    static constexpr int kThreads = kQ == 1 ? 512 : 1024;
-    static constexpr int kMinBlocks = kQ == 1 ? 2 : 1;
+    static constexpr int kPair = (kQ == 1 && TVZ_Q1_WIDE) ? 2 : 1;   // adjacent tiles one CTA works on
+    static constexpr int kThreads = (kQ == 1 && !TVZ_Q1_WIDE) ? 512 : 1024;
+    static constexpr int kMinBlocks = (kQ == 1 && !TVZ_Q1_WIDE) ? 2 : 1;
     static constexpr int kWarps = kThreads / 32;
-    static constexpr int kQueue = kQ == 1 ? 128 : 64;             // survivors parked per warp
+    static constexpr int kQueue = (kQ == 1 && !TVZ_Q1_WIDE) ? 128 : 64;   // survivors parked per warp
     static constexpr int kKeys = kQ == 1 ? kTileKeys : kParamKeys;
-    static constexpr int kCountWords = kQ == 1 ? kTileRows : kQ * kTileRows / 2;  // batch: two 16-bit counts per word
-    static constexpr int kRowsPerThread = kTileRows / kThreads;
+    static constexpr int kRows = kTileRows * kPair;               // rows whose counts the CTA keeps
+    static constexpr int kCountWords = kQ == 1 ? kRows : kQ * kRows / 2;  // batch: two 16-bit counts per word
+    static constexpr int kRowsPerThread = kRows / kThreads;
     static constexpr int kGroup = kThreads / kQ;                  // threads that poll the predecessors of one query
 };
 
@@ -155,7 +162,6 @@ struct TileArgs {
     unsigned *ctrl;                         // {finished CTAs} (fused gather only)
     unsigned seq;                           // this query's sequence number on its workspace (1..65535)
     int uniform_units;                      // > 0: packed tile t starts at unit t * uniform_units (no lookup before the first loads)
-    const unsigned *my_flags;               // fused gather: this rank's flags, written by the peers
     long long *trace;                       // debug: [n_tiles][16] phase timestamps (tvz_debug_tile_trace), normally null
     long long n_pos, n_rows_cap;            // checked build: arranged positions / rows the arrays hold
     GatherTargets gt;
@@ -183,6 +189,30 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Tagged 16-byte record entries of the fused gather: {v.x, epoch, v.y, epoch}.  The store may be split in
+// transit, but each 8-byte half is atomic and carries its own tag.
+__device__ __forceinline__ void st_tagged(int *entry, int2 v, unsigned epoch) {
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(entry), "r"(v.x), "r"(epoch), "r"(v.y) : "memory");
+}
+// One look at an entry: are both halves there?
+__device__ __forceinline__ bool try_tagged(const int *entry, unsigned epoch) {
+    unsigned a0, t0, a1, t1;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(t0), "=r"(a1), "=r"(t1) : "l"(entry) : "memory");
+    return t0 == epoch && t1 == epoch;
+}
+// Poll (bounded) until both halves of an entry carry `epoch`; returns the two values.
+__device__ __forceinline__ int2 ld_tagged(const int *entry, unsigned epoch) {
+    unsigned polls = 0;
+    while (true) {
+        unsigned a0, t0, a1, t1;
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(a0), "=r"(t0) : "l"(entry) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(a1), "=r"(t1) : "l"(entry + 2) : "memory");
+        if (t0 == epoch && t1 == epoch) return make_int2(static_cast<int>(a0), static_cast<int>(a1));
+        if (++polls > 1024) __nanosleep(64);
+        if (polls == (1u << 25)) __trap();   // a peer that never answers turns into a launch failure, not a hung GPU
+    }
+}
+
 // How a predecessor's total is polled.  TVZ_POLL_LD: 0 = ld.relaxed.gpu (a strong load per lane), 1 = ld.global.cg
 // (L2-only weak load, volatile asm so that the loop re-reads; the warp's lanes coalesce into line requests)
 #ifndef TVZ_POLL_LD
@@ -235,7 +265,9 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem<kQ> &sm = *reinterpret_cast<TileSmem<kQ> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x;                    // this CTA's place in the exchange (= its tile, or its pair of tiles)
+    const int t0 = tile * S::kPair;                 // first tile of the CTA
+    const bool last_cta = tile == static_cast<int>(gridDim.x) - 1;
     const int nq = kQ == 1 ? 1 : a.n_queries;
     auto mark = [&](int k) {   // debug trace: slot 0 = global ns at CTA start, slots 1..7 = SM cycles at the phase ends
         if (a.trace && tid == 0) {
@@ -251,17 +283,23 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
     // ---- prologue: nothing here depends on the previous kernel of the stream ----
     // The tile descriptor is on its way while the byte map and the counts are zeroed; the first
     // fingerprint loads follow it (they do not depend on the query either).
-    const bool in_tail = a.tail_index >= 0 && tile >= a.tail_index;
+    const bool in_tail = a.tail_index >= 0 && t0 >= a.tail_index;
     const bool uniform = a.uniform_units > 0 && !in_tail;
     TileDesc td;
-    if (in_tail) td = a.tail[tile - a.tail_index];
-    else td = a.tiles[tile];
+    if (in_tail) td = a.tail[t0 - a.tail_index];
+    else td = a.tiles[t0];
+    if (S::kPair == 2 && t0 + 1 < a.n_tiles) {      // rows and units of adjacent tiles are contiguous: one merged range
+        const int t1 = t0 + 1;
+        const TileDesc d1 = (a.tail_index >= 0 && t1 >= a.tail_index) ? a.tail[t1 - a.tail_index] : a.tiles[t1];
+        td.n_rows += d1.n_rows;
+        td.unit_hi = max(td.unit_hi, d1.unit_hi);
+    }
     const bool resident = kQ > 1 || a.n_keys <= S::kKeys;   // the query's keys fit shared memory
     const bool scan = kQ > 1 || a.n_keys > 0;               // an empty query matches nothing: no stream
     // Packed tiles start at a unit that is pure arithmetic (tile * uniform_units), so the first
     // fingerprint loads -- which do not depend on the query either -- leave before anything has been
     // read; the array is padded so that they are in bounds even where a tile turns out to be shorter.
-    const unsigned unit_lo = uniform ? static_cast<unsigned>(tile) * static_cast<unsigned>(a.uniform_units) : td.unit_lo;
+    const unsigned unit_lo = uniform ? static_cast<unsigned>(t0) * static_cast<unsigned>(a.uniform_units) : td.unit_lo;
     const unsigned short *lane_fp = a.fp + lane * 16;
     U32x8 v[2];
     if (uniform && scan) {
@@ -274,10 +312,10 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
     for (int i = tid; i < S::kCountWords / 4; i += S::kThreads)
         reinterpret_cast<uint4 *>(sm.counts)[i] = make_uint4(0u, 0u, 0u, 0u);
     const unsigned unit_hi = scan ? td.unit_hi : unit_lo;
-    TVZ_CHECK(td.n_rows >= 0 && td.n_rows <= kTileRows && td.row_lo >= 0 && td.row_lo + td.n_rows <= a.n_rows_cap);
+    TVZ_CHECK(td.n_rows >= 0 && td.n_rows <= S::kRows && td.row_lo >= 0 && td.row_lo + td.n_rows <= a.n_rows_cap);
     TVZ_CHECK(td.unit_hi >= td.unit_lo && static_cast<long long>(td.unit_hi) * kFpPerUnit <= a.n_pos);
     TVZ_CHECK(!uniform || td.unit_lo == unit_lo);
-    TVZ_CHECK(tile < a.n_tiles && (kQ > 1 || a.n_keys >= 0));
+    TVZ_CHECK(t0 < a.n_tiles && (kQ > 1 || a.n_keys >= 0));
     if (!uniform) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -336,7 +374,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
                 if (lo >= a.n_keys || __ldg(a.keys_g + lo) != val) return;
                 m = __ldg(a.mult_g + lo);
             }
-            TVZ_CHECK(local < static_cast<unsigned>(kTileRows));
+            TVZ_CHECK(local < static_cast<unsigned>(S::kRows));
             atomicAdd(&sm.counts[local], static_cast<unsigned>(m));
         } else {
             unsigned qm = sm.map[filter_hash(val)];
@@ -450,8 +488,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
     // A tile without a single qualifying row (most tiles of a selective query) has nothing to place: it
     // needs no offset, polls nothing and is done -- only the last tile always goes on (it writes the header).
     __syncthreads();
-    bool shipped = false;   // this thread stored something into a peer
-    bool idle = tile != a.n_tiles - 1;
+    bool idle = !last_cta;
     for (int b = 0; b < nq; ++b) idle = idle && sm.agg[b] == 0;
     if (!idle) {   // hits of all earlier tiles
         const unsigned seq = a.seq;
@@ -471,98 +508,95 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (lane == 0) sm.part[warp] = sum;
-    __syncthreads();
-    mark(8);
-    if (tid < nq) {
-        constexpr int kWarpsPerGroup = S::kGroup / 32;
-        unsigned long long e = 0;
-        for (int w = 0; w < kWarpsPerGroup; ++w) e += sm.part[tid * kWarpsPerGroup + w];
-        sm.excl[tid] = e;
-        if (tile == a.n_tiles - 1) {   // the last tile knows every query's total
-            const long long total = static_cast<long long>(e) + sm.agg[tid];
-            a.n_hits_out[tid] = total;
-            int *o = a.out + tid * a.out_stride;
-            const int2 hdr = make_int2(total > 0x7fffffffll ? 0x7fffffff : static_cast<int>(total), total > a.cap ? 1 : 0);
-            *reinterpret_cast<int2 *>(o) = hdr;
-            for (int p = 0; p < a.gt.n_peers; ++p)   // fused gather: the header travels like any hit
-                *reinterpret_cast<int2 *>(a.gt.record[p] + tid * a.gt.query_stride) = hdr;
-        }
-    }
-    __syncthreads();
-    mark(9);
-    for (int b = 0; b < nq; ++b) {
-        int cnt[S::kRowsPerThread];
-        int mine = 0;
-#pragma unroll
-        for (int j = 0; j < S::kRowsPerThread; ++j) {
-            cnt[j] = count_of(b, r0 + j);
-            if (qualifies(cnt[j], r0 + j)) ++mine; else cnt[j] = -1;   // counts are never negative
-        }
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        long long pos = static_cast<long long>(sm.excl[b]) + sm.warp_tot[b][warp] + (incl - mine);
-        int *o = a.out + b * a.out_stride;
-#pragma unroll
-        for (int j = 0; j < S::kRowsPerThread; ++j) {
-            if (cnt[j] >= 0) {
-                TVZ_CHECK(pos >= 0);
-                if (pos < a.cap) {
-                    const int row = td.row_lo + r0 + j;
-                    TVZ_CHECK(row < a.n_rows_cap && r0 + j < td.n_rows);
-                    const int2 hit = make_int2(a.vid[row], cnt[j]);
-                    *reinterpret_cast<int2 *>(o + 2 + 2 * pos) = hit;
-                    if (kQ == 1 && a.rows_out) a.rows_out[pos] = row;
-                    // fused gather: every CTA ships its own hits to all peers (8-byte stores over NVLink), in parallel
-                    for (int p = 0; p < a.gt.n_peers; ++p)
-                        *reinterpret_cast<int2 *>(a.gt.record[p] + b * a.gt.query_stride + 2 + 2 * pos) = hit;
-                    shipped = a.gt.n_peers > 0;
-                }
-                ++pos;
+        __syncthreads();
+        mark(8);
+        if (tid < nq) {
+            constexpr int kWarpsPerGroup = S::kGroup / 32;
+            unsigned long long e = 0;
+            for (int w = 0; w < kWarpsPerGroup; ++w) e += sm.part[tid * kWarpsPerGroup + w];
+            sm.excl[tid] = e;
+            if (last_cta) {   // the last tile knows every query's total
+                const long long total = static_cast<long long>(e) + sm.agg[tid];
+                a.n_hits_out[tid] = total;
+                int *o = a.out + tid * a.out_stride;
+                const int2 hdr = make_int2(total > 0x7fffffffll ? 0x7fffffff : static_cast<int>(total), total > a.cap ? 1 : 0);
+                *reinterpret_cast<int2 *>(o) = hdr;
+                for (int p = 0; p < a.gt.n_dst; ++p)   // fused gather: the header travels like any hit, as entry 0
+                    st_tagged(a.gt.record[p] + tid * a.gt.query_stride, hdr, a.gt.epoch);
             }
         }
-    }
+        __syncthreads();
+        mark(9);
+        for (int b = 0; b < nq; ++b) {
+            int cnt[S::kRowsPerThread];
+            int mine = 0;
+#pragma unroll
+            for (int j = 0; j < S::kRowsPerThread; ++j) {
+                cnt[j] = count_of(b, r0 + j);
+                if (qualifies(cnt[j], r0 + j)) ++mine; else cnt[j] = -1;   // counts are never negative
+            }
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            long long pos = static_cast<long long>(sm.excl[b]) + sm.warp_tot[b][warp] + (incl - mine);
+            int *o = a.out + b * a.out_stride;
+#pragma unroll
+            for (int j = 0; j < S::kRowsPerThread; ++j) {
+                if (cnt[j] >= 0) {
+                    TVZ_CHECK(pos >= 0);
+                    if (pos < a.cap) {
+                        const int row = td.row_lo + r0 + j;
+                        TVZ_CHECK(row < a.n_rows_cap && r0 + j < td.n_rows);
+                        const int2 hit = make_int2(a.vid[row], cnt[j]);
+                        *reinterpret_cast<int2 *>(o + 2 + 2 * pos) = hit;
+                        if (kQ == 1 && a.rows_out) a.rows_out[pos] = row;
+                        // fused gather: every CTA ships its own hits to all peers as it finds them (NVLink stores, in
+                        // parallel across CTAs), each 8-byte half tagged with the query epoch
+                        for (int p = 0; p < a.gt.n_dst; ++p)
+                            st_tagged(a.gt.record[p] + b * a.gt.query_stride + 4 * (1 + pos), hit, a.gt.epoch);
+                    }
+                    ++pos;
+                }
+            }
+        }
     }   // !idle
     mark(10);
 
-    // ---- fused gather: the CTA that finishes last raises this rank's flag on every peer ----
-    // A CTA that stored something into the peers fences it at system scope (one NVLink round trip,
-    // measured ~1.8 us; the CTAs do it in parallel, and most tiles of a selective query ship nothing and
-    // skip it) before it counts itself done; the last one fences once more and raises the flags, then
-    // waits (bounded) until the flags of all peers show this query.
-    if (a.gt.n_peers == 0) return;   // (the query sequence number comes from the host: nothing to re-arm)
-    const int any_shipped = __syncthreads_or(shipped || (tile == a.n_tiles - 1 && tid < nq));   // (the header is peer traffic too)
+    // ---- fused gather: the last CTAs wait until every peer's record for this query is complete here ----
+    // Records travel in a tagged form (the LL idea of collective libraries): entry e of a record is 16 bytes
+    // {value0, epoch, value1, epoch} -- entry 0 = {n_hits, overflow}, entry 1 + h = {video_id, match_count} -- and
+    // each 8-byte half is stored atomically, so a reader that sees the epoch in both halves has the data.  Senders
+    // therefore need no system-scope fence, no done-counter and no flag: CTAs just store and exit.  The receivers
+    // are the LAST n_peers CTAs of the grid, one peer each: the whole CTA polls the header of that peer's slot in
+    // this rank's OWN memory, then sweeps the hit entries (four independent 16-byte loads per thread and round; an
+    // entry that is not there yet is polled, bounded).  When the kernel completes, all records are complete here.
+    if (a.gt.n_peers == 0) return;
+    const int back = static_cast<int>(gridDim.x) - 1 - tile;            // 0 for the last CTA
+    const int n_recv = min(static_cast<int>(gridDim.x), a.gt.n_peers);
+    if (back >= n_recv) return;
     mark(11);
-    if (warp != 0) return;
-    unsigned last = 0;
-    if (lane == 0) {
-        if (any_shipped) __threadfence_system();
-        else __threadfence();
-        last = atomicAdd(a.ctrl, 1u) == gridDim.x - 1;
-        if (last) a.ctrl[0] = 0;
+    for (int p = back; p < a.gt.n_peers; p += n_recv) {
+        for (int b = 0; b < nq; ++b) {
+            const int *slot = a.gt.my_slots + p * a.gt.slot_stride + b * a.gt.query_stride;
+            const int2 hdr = ld_tagged(slot, a.gt.epoch);                   // (every thread polls the header: same address)
+            const long long n = min(static_cast<long long>(hdr.x), a.cap);
+            for (long long i0 = tid; i0 < n; i0 += 4 * S::kThreads) {
+                bool there[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long i = i0 + u * S::kThreads;
+                    there[u] = i >= n || try_tagged(slot + 4 * (1 + i), a.gt.epoch);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (!there[u]) (void)ld_tagged(slot + 4 * (1 + i0 + u * S::kThreads), a.gt.epoch);
+            }
+        }
     }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (!last) return;
-    mark(12);
-    if (lane < a.gt.n_peers) {
-        __threadfence_system();   // every CTA's peer stores happen before its count, the counts before this fence
-        mark(13);
-        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.gt.flag[lane]), "r"(a.gt.epoch) : "memory");
-        mark(14);
-        // The peers' records are in this GPU's memory once their flags are: whatever reads them runs after this
-        // kernel has completed, so the poll needs no fence of its own.
-        unsigned f, polls = 0;
-        do {
-            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(a.my_flags + lane) : "memory");
-            if (f == a.gt.epoch) break;
-            if (++polls > 256) __nanosleep(64);
-            if (polls == (1u << 26)) __trap();
-        } while (true);
-        mark(15);
-    }
+    mark(15);
 }
 
 // Per hit row: the 1-based query index at which the row reaches min_match.
@@ -993,8 +1027,7 @@ int wait_for_mutations(const tvz_catalog *cat, tvz_match_ws *ws, const CatView &
 
 // Enqueue query upload + the tile kernel (+ kth) on `st`.  `want_kth` needs qn <= q_cap.
 int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn, int min_match, bool want_kth,
-                  int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr,
-                  const unsigned *my_flags = nullptr) {
+                  int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr) {
     TVZ_REQUIRE(cat && ws && ws->cat == cat, "workspace does not belong to this catalogue");
     TVZ_REQUIRE(qn >= 0 && (qn == 0 || h_q), "bad query");
     if (!d_out) {
@@ -1052,10 +1085,7 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
         a.out = d_out;
         a.out_stride = 0;
         a.rows_out = ws->d_rows;
-        if (gather) {
-            a.gt = *gather;
-            a.my_flags = my_flags;
-        }
+        if (gather) a.gt = *gather;
         const bool param = nk <= kParamKeys;
         if (!param) {
             TVZ_CUDA(cudaMemcpyAsync(ws->d_keys, h_keys, sizeof(unsigned long long) * nk, cudaMemcpyHostToDevice, st));
@@ -1065,7 +1095,7 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
             staged_copy = true;
         }
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
-        const dim3 grid(static_cast<unsigned>(cv.n_tiles)), block(TileShape<1>::kThreads);
+        const dim3 grid(static_cast<unsigned>((cv.n_tiles + TileShape<1>::kPair - 1) / TileShape<1>::kPair)), block(TileShape<1>::kThreads);
         if (param) {
             SmallQuery sq;
             memcpy(sq.keys, h_keys, sizeof(unsigned long long) * nk);
@@ -1105,8 +1135,7 @@ int ensure_batch_buffers(tvz_match_ws *ws) {
 // Up to kBatch queries in one pass: keys staged with ONE copy, one kernel; records land in
 // d_out [nb][out_stride] (NULL: the workspace's own b_out with out_stride = 2 * (cap + 1)).
 int enqueue_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all, const int64_t *q_off, int g0, int nb,
-                  int min_match, int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr,
-                  const unsigned *my_flags = nullptr) {
+                  int min_match, int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr) {
     TVZ_REQUIRE(nb >= 1 && nb <= kBatch, "a batch holds 1..%d queries", kBatch);
     int rc = ensure_batch_buffers(ws);
     if (rc) return rc;
@@ -1175,8 +1204,7 @@ int enqueue_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
     a.rows_out = nullptr;
     if (gather) {
         a.gt = *gather;
-        a.gt.query_stride = a.out_stride;
-        a.my_flags = my_flags;
+        a.gt.query_stride = 4 * (out_cap + 1);   // tagged entries are 4 ints
     }
     if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
     TVZ_CUDA(launch_pdl(match_tile_kernel<kBatch, false>, dim3(static_cast<unsigned>(cv.n_tiles)),
@@ -1185,15 +1213,20 @@ int enqueue_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
     return TVZ_OK;
 }
 
-int make_gather(int n_peers, const uint64_t *peer_record, const uint64_t *peer_flag, const uint32_t *d_my_flags,
+int make_gather(int n_peers, int n_dst, const uint64_t *peer_record, const int32_t *d_my_slots, int64_t slot_stride_ints,
                 uint32_t epoch, GatherTargets &gt) {
     TVZ_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers, "n_peers %d outside [1, %d]", n_peers, kMaxPeers);
-    TVZ_REQUIRE(peer_record && peer_flag && d_my_flags, "null pointer");
+    TVZ_REQUIRE(n_dst == n_peers || n_dst == 1, "peer_record holds one address per peer, or one multicast address");
+    TVZ_REQUIRE(peer_record && d_my_slots && slot_stride_ints > 0 && slot_stride_ints % 4 == 0, "bad gather buffers");
+    TVZ_REQUIRE(epoch != 0, "epoch 0 is what fresh gather buffers carry");
     gt.n_peers = n_peers;
+    gt.n_dst = n_dst;
     gt.epoch = epoch;
-    for (int p = 0; p < n_peers; ++p) {
+    gt.my_slots = d_my_slots;
+    gt.slot_stride = slot_stride_ints;
+    for (int p = 0; p < n_dst; ++p) {
+        TVZ_REQUIRE(peer_record[p] % 16 == 0, "gather slots must be 16-byte aligned");
         gt.record[p] = reinterpret_cast<int *>(static_cast<uintptr_t>(peer_record[p]));
-        gt.flag[p] = reinterpret_cast<unsigned *>(static_cast<uintptr_t>(peer_flag[p]));
     }
     return TVZ_OK;
 }
@@ -1689,15 +1722,16 @@ int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const doub
 }
 
 int tvz_catalog_match_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn,
-                                   int min_match, int n_peers, const uint64_t *peer_record, const uint64_t *peer_flag,
-                                   const uint32_t *d_my_flags, int64_t out_cap, uint32_t epoch, void *stream) {
+                                   int min_match, int n_peers, int n_dst, const uint64_t *peer_record,
+                                   const int32_t *d_my_slots, int64_t slot_stride_ints, int64_t out_cap, uint32_t epoch,
+                                   void *stream) {
     return guarded([&]() -> int {
     TVZ_REQUIRE(cat && cat->max_tiles() > 0, "the fused gather needs a non-empty shard");
+    TVZ_REQUIRE(slot_stride_ints >= 4 * (out_cap + 1), "a gather slot holds 4 * (out_cap + 1) ints");
     GatherTargets gt;
-    int rc = make_gather(n_peers, peer_record, peer_flag, d_my_flags, epoch, gt);
+    int rc = make_gather(n_peers, n_dst, peer_record, d_my_slots, slot_stride_ints, epoch, gt);
     if (rc) return rc;
-    return enqueue_match(cat, ws, h_q, qn, min_match, false, nullptr, out_cap, static_cast<cudaStream_t>(stream), &gt,
-                         d_my_flags);
+    return enqueue_match(cat, ws, h_q, qn, min_match, false, nullptr, out_cap, static_cast<cudaStream_t>(stream), &gt);
     });
 }
 
@@ -1771,18 +1805,19 @@ int tvz_catalog_match_batch_async(const tvz_catalog *cat, tvz_match_ws *ws, cons
 }
 
 int tvz_catalog_match_batch_gather_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
-                                         const int64_t *q_off, int n_queries, int min_match, int n_peers,
-                                         const uint64_t *peer_record, const uint64_t *peer_flag,
-                                         const uint32_t *d_my_flags, int64_t out_cap, uint32_t epoch, void *stream) {
+                                         const int64_t *q_off, int n_queries, int min_match, int n_peers, int n_dst,
+                                         const uint64_t *peer_record, const int32_t *d_my_slots,
+                                         int64_t slot_stride_ints, int64_t out_cap, uint32_t epoch, void *stream) {
     return guarded([&]() -> int {
     TVZ_REQUIRE(cat && ws && ws->cat == cat, "workspace does not belong to this catalogue");
     TVZ_REQUIRE(cat->max_tiles() > 0, "the fused gather needs a non-empty shard");
     TVZ_REQUIRE(q_off && (q_all || q_off[n_queries] == 0), "bad arguments");
+    TVZ_REQUIRE(slot_stride_ints >= static_cast<int64_t>(kBatch) * 4 * (out_cap + 1), "a batched gather slot holds 8 * 4 * (out_cap + 1) ints");
     GatherTargets gt;
-    int rc = make_gather(n_peers, peer_record, peer_flag, d_my_flags, epoch, gt);
+    int rc = make_gather(n_peers, n_dst, peer_record, d_my_slots, slot_stride_ints, epoch, gt);
     if (rc) return rc;
     return enqueue_batch(cat, ws, q_all, q_off, 0, n_queries, min_match, nullptr, out_cap, static_cast<cudaStream_t>(stream),
-                         &gt, d_my_flags);
+                         &gt);
     });
 }
 

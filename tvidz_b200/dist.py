@@ -58,7 +58,7 @@ class _SymmetricRecords:
     """Double-buffered gather buffers in symmetric memory: 2 sets x [world] records of `rec_ints`
     int32 each, then 2 sets x [world] flags.  Rank r's record lives in slot r of every rank's buffer."""
 
-    def __init__(self, rec_ints: int, device, group):
+    def __init__(self, rec_ints: int, device, group, multicast: bool = False):
         import torch.distributed._symmetric_memory as symm
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -72,8 +72,17 @@ class _SymmetricRecords:
         torch.cuda.synchronize(device)
         self.hdl.barrier()
         base = np.asarray([int(p) for p in self.hdl.buffer_ptrs], np.uint64)
-        self.peer_record, self.peer_flag, self.my_flags, self.views = [], [], [], []
+        # NVSwitch multicast mapping of the same buffer, if the platform offers one: a store to it lands in every rank's copy
+        try:
+            self.multicast = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if multicast else 0
+        except Exception:
+            self.multicast = 0
+        self.peer_record, self.peer_flag, self.my_flags, self.views, self.my_slots, self.mc_record = [], [], [], [], [], []
         for s in range(2):
+            self.my_slots.append(int(base[self.rank]) + 4 * (s * self.world * self.rec_ints))
+            if self.multicast:      # ONE address for this rank's slot in everybody's buffer (the layout is symmetric)
+                self.mc_record.append(np.asarray(
+                    [self.multicast + 4 * (s * self.world * self.rec_ints + self.rank * self.rec_ints)], np.uint64))
             self.peer_record.append(np.ascontiguousarray(
                 base + np.uint64(4 * (s * self.world * self.rec_ints + self.rank * self.rec_ints))))
             self.peer_flag.append(np.ascontiguousarray(base + np.uint64(4 * (n_rec + s * self.world + self.rank))))
@@ -103,7 +112,8 @@ class ShardedCatalogue:
     """
 
     def __init__(self, ts, off, video_id, hit_capacity: int = 1 << 15, device=None,
-                 local_factory: Callable | None = None, group=None, gather: str = "nccl", presharded: bool = False):
+                 local_factory: Callable | None = None, group=None, gather: str = "nccl", presharded: bool = False,
+                 multicast: bool = True):
         """`presharded=True`: (ts, off, video_id) already ARE this rank's shard (catalogues too large to
         materialise on every rank); shards concatenate in rank order."""
         self.group = group
@@ -137,6 +147,7 @@ class ShardedCatalogue:
         if gather == "fused" and min(h - l for l, h in self.bounds) == 0:
             gather = "nccl"                       # an empty shard cannot run the fused epilogue
         self.gather = gather
+        self.multicast = bool(multicast)          # fused gather: ship through the NVSwitch multicast mapping when there is one
         self.n_rows_local = hi - lo
         self.n_values_local = int(s_off[-1]) if s_off.size else 0
         self.batch = 8
@@ -144,30 +155,33 @@ class ShardedCatalogue:
 
     # ---- buffers -------------------------------------------------------------------------
     def _alloc(self, cap: int) -> None:
-        self.cap = int(cap) | 1                               # odd capacity: (cap + 1) * 2 ints is a 16-byte multiple
-        self.rec_ints = (self.cap + 1) * 2
+        self.cap = int(cap)
+        # ints per record entry: 2 = (value0, value1) for NCCL; 4 = (value0, epoch, value1, epoch), the tagged form the
+        # fused gather ships (every 8-byte half carries the query epoch: complete when all tags are there)
+        self.ent = 4 if self.gather == "fused" else 2
+        self.rec_ints = (self.cap + 1) * self.ent
         self._sym = self._sym_b = None
         self._host = _host_mirror(self.world * self.rec_ints, self._cuda)
-        self._host_np = self._host.numpy().reshape(self.world, self.cap + 1, 2)
+        self._host_np = self._host.numpy().reshape(self.world, self.cap + 1, self.ent)
         self._host_b = self._host_b_np = None
         if self.gather == "nccl":
             self.record = torch.zeros((self.cap + 1, 2), dtype=torch.int32, device=self.device)
             self.gathered = torch.zeros((self.world * (self.cap + 1), 2), dtype=torch.int32, device=self.device)
             self.record_b = self.gathered_b = None
             return
-        self._sym = _SymmetricRecords(self.rec_ints, self.device, self.group)
+        self._sym = _SymmetricRecords(self.rec_ints, self.device, self.group, multicast=self.multicast)
 
     def _alloc_batch(self) -> None:
         if self._host_b is None:
             self._host_b = _host_mirror(self.world * self.batch * self.rec_ints, self._cuda)
-            self._host_b_np = self._host_b.numpy().reshape(self.world, self.batch, self.cap + 1, 2)
+            self._host_b_np = self._host_b.numpy().reshape(self.world, self.batch, self.cap + 1, self.ent)
         if self.gather == "nccl":
             if self.record_b is None:
                 self.record_b = torch.zeros((self.batch, self.cap + 1, 2), dtype=torch.int32, device=self.device)
                 self.gathered_b = torch.zeros((self.world, self.batch, self.cap + 1, 2), dtype=torch.int32,
                                               device=self.device)
         elif self._sym_b is None:
-            self._sym_b = _SymmetricRecords(self.batch * self.rec_ints, self.device, self.group)
+            self._sym_b = _SymmetricRecords(self.batch * self.rec_ints, self.device, self.group, multicast=self.multicast)
 
     def _regrow(self, needed: int) -> None:
         if self.gather == "fused":
@@ -178,35 +192,38 @@ class ShardedCatalogue:
     # ---- one query -----------------------------------------------------------------------
     def enqueue(self, new_timestamps, min_match: int) -> torch.Tensor:
         """Local count + compaction + the gather, all on the current stream; returns the device
-        tensor [world, cap + 1, 2] that holds every shard's record once the stream gets there."""
+        tensor [world, cap + 1, ent] that holds every shard's record once the stream gets there
+        (ent = 2: (value0, value1); fused gather: ent = 4, (value0, epoch, value1, epoch))."""
         if self.gather == "nccl":
             self.local.match_async(new_timestamps, min_match, self.record)
             dist.all_gather_into_tensor(self.gathered, self.record, group=self.group)
             return self.gathered.view(self.world, self.cap + 1, 2)
         sy = self._sym
         s, epoch = sy.next()
-        self.local.match_gather_async(new_timestamps, min_match, sy.peer_record[s], sy.peer_flag[s], sy.my_flags[s],
+        dst = sy.mc_record[s] if sy.multicast else sy.peer_record[s]
+        self.local.match_gather_async(new_timestamps, min_match, self.world, dst, sy.my_slots[s], self.rec_ints,
                                       self.cap, epoch)
-        return sy.views[s].view(self.world, self.cap + 1, 2)
+        return sy.views[s].view(self.world, self.cap + 1, self.ent)
 
     def _read(self, g: torch.Tensor, host: torch.Tensor, host_np: np.ndarray, n_records: int, stride: int):
         """Every record's header + an optimistic first slice of its hits in ONE device-to-host copy; the
-        rest (rare) in a second one.  -> (headers [n_records, 2], overflowed)"""
+        rest (rare) in a second one.  -> headers int32 [n_records, 2] = (n_hits, overflow)"""
         first = min(self.cap, 1024)
-        flat = host_np.reshape(n_records, self.cap + 1, 2)
+        eb = 4 * self.ent                                         # bytes per entry
+        flat = host_np.reshape(n_records, self.cap + 1, self.ent)
         if self._cuda:
             from ._lib import check, lib
             st = int(torch.cuda.current_stream(self.device).cuda_stream)
             check(lib().tvz_copy_records_to_host(g.data_ptr(), host.data_ptr(), n_records, 4 * stride, 0,
-                                                 8 * (first + 1), 1, st))
-            heads = flat[:, 0, :]
+                                                 eb * (first + 1), 1, st))
+            heads = flat[:, 0, ::self.ent // 2]
             n_max = int(heads[:, 0].max())
             if not heads[:, 1].any() and first < n_max <= self.cap:
                 check(lib().tvz_copy_records_to_host(g.data_ptr(), host.data_ptr(), n_records, 4 * stride,
-                                                     8 * (first + 1), 8 * (n_max - first), 1, st))
+                                                     eb * (first + 1), eb * (n_max - first), 1, st))
         else:
             host.copy_(g.reshape(-1))
-            heads = flat[:, 0, :]
+            heads = flat[:, 0, ::self.ent // 2]
         return heads
 
     def find_duplicates(self, new_timestamps, min_match: int = 5) -> list[tuple[int, int]]:
@@ -221,14 +238,15 @@ class ShardedCatalogue:
                 continue
             flat: list = []
             host = self._host_np
+            step = self.ent // 2
             for r, (n, _) in enumerate(hl):                       # shards in rank order = catalogue order
                 if n:
-                    flat += host[r, 1:1 + n].ravel().tolist()
+                    flat += host[r, 1:1 + n, ::step].ravel().tolist()
             return list(zip(flat[0::2], flat[1::2]))
 
     # ---- 8 queries per pass --------------------------------------------------------------
     def enqueue_many(self, queries, min_match: int) -> torch.Tensor:
-        """Up to 8 queries answered by ONE pass over every shard -> device tensor [world, 8, cap + 1, 2]."""
+        """Up to 8 queries answered by ONE pass over every shard -> device tensor [world, 8, cap + 1, ent]."""
         if len(queries) > self.batch:
             raise ValueError("a batch holds at most %d queries" % self.batch)
         self._alloc_batch()
@@ -238,9 +256,10 @@ class ShardedCatalogue:
             return self.gathered_b
         sy = self._sym_b
         s, epoch = sy.next()
-        self.local.match_batch_gather_async(queries, min_match, sy.peer_record[s], sy.peer_flag[s], sy.my_flags[s],
-                                            self.cap, epoch)
-        return sy.views[s].view(self.world, self.batch, self.cap + 1, 2)
+        dst = sy.mc_record[s] if sy.multicast else sy.peer_record[s]
+        self.local.match_batch_gather_async(queries, min_match, self.world, dst, sy.my_slots[s],
+                                            self.batch * self.rec_ints, self.cap, epoch)
+        return sy.views[s].view(self.world, self.batch, self.cap + 1, self.ent)
 
     def match_many(self, queries, min_match: int = 5) -> list[np.ndarray]:
         """[int32 [n_i, 2] (video_id, match_count) in catalogue order for every query], 8 queries per
@@ -258,7 +277,7 @@ class ShardedCatalogue:
                 self._regrow(n_max)
                 continue
             for b in range(len(group)):
-                pairs, _, _ = merge_records(self._host_b_np[:, b, :n_max + 1, :], self.cap)
+                pairs, _, _ = merge_records(self._host_b_np[:, b, :n_max + 1, ::self.ent // 2], self.cap)
                 out[g0 + b] = pairs
             g0 += len(group)
         return out
