@@ -32,6 +32,11 @@ def rows_to_csr(rows: Iterable[tuple[int, Sequence[float]]]):
     return ts, off, np.fromiter((vid for vid, _ in rows), np.int32, len(rows))
 
 
+def _ptr(a: np.ndarray) -> int:
+    """Data pointer of a contiguous array (cheaper than a.ctypes.data)."""
+    return a.__array_interface__["data"][0]
+
+
 def _as_query(q) -> np.ndarray:
     if isinstance(q, np.ndarray) and q.dtype == np.float64 and q.ndim == 1 and q.flags.c_contiguous:
         return q
@@ -40,13 +45,14 @@ def _as_query(q) -> np.ndarray:
 
 class _Workspace:
     """One tvz_match_ws plus the host arrays its synchronous calls fill."""
-    __slots__ = ("handle", "cap", "vid", "cnt", "kth")
+    __slots__ = ("handle", "cap", "vid", "cnt", "kth", "p_vid", "p_cnt", "p_kth")
 
     def __init__(self, handle, cap):
         self.handle, self.cap = handle, cap
         self.vid = np.empty(cap, np.int32)
         self.cnt = np.empty(cap, np.int32)
         self.kth = np.empty(cap, np.int32)
+        self.p_vid, self.p_cnt, self.p_kth = _ptr(self.vid), _ptr(self.cnt), _ptr(self.kth)
 
 
 class Catalogue:
@@ -153,8 +159,7 @@ class Catalogue:
         """Replace (or append) the row of `video_id` on the device.  False: the tail is full -- repack.
         The caller keeps queries out while this runs (Inspector does)."""
         q = _as_query(timestamps)
-        with torch.cuda.device(self.device):
-            rc = lib().tvz_catalog_upsert(self._handle, int(video_id), q.ctypes.data, q.shape[0])
+        rc = lib().tvz_catalog_upsert(self._handle, int(video_id), _ptr(q), q.shape[0])     # (runs on the catalogue's device)
         if rc == TVZ_ERR_OVERFLOW:
             return False
         check(rc)
@@ -169,10 +174,8 @@ class Catalogue:
         while True:
             ws = self._checkout(need)
             try:
-                with torch.cuda.device(self.device):
-                    rc = lib().tvz_catalog_match(self._handle, ws.handle, q.ctypes.data, q.shape[0], int(min_match),
-                                                 ws.vid.ctypes.data, ws.cnt.ctypes.data,
-                                                 ws.kth.ctypes.data if with_kth else None, ws.cap, C.byref(n_out))
+                rc = lib().tvz_catalog_match(self._handle, ws.handle, _ptr(q), q.shape[0], int(min_match),
+                                             ws.p_vid, ws.p_cnt, ws.p_kth if with_kth else None, ws.cap, C.byref(n_out))
                 if rc == TVZ_ERR_OVERFLOW and n_out.value > ws.cap:
                     need = int(n_out.value)          # grow the workspace and run the query again
                     continue
@@ -255,9 +258,8 @@ class Catalogue:
         cap = out.shape[0] - 1
         q = _as_query(new_timestamps)
         ws = self._ws_async(cap)
-        with torch.cuda.device(self.device):
-            check(lib().tvz_catalog_match_async(self._handle, ws.handle, q.ctypes.data, q.shape[0], int(min_match),
-                                                out.data_ptr(), cap, self._stream(stream)))
+        check(lib().tvz_catalog_match_async(self._handle, ws.handle, _ptr(q), q.shape[0], int(min_match),
+                                            out.data_ptr(), cap, self._stream(stream)))
 
     @staticmethod
     def _pack_queries(queries):
@@ -291,11 +293,10 @@ class Catalogue:
         multicast address that reaches all peers."""
         q = _as_query(new_timestamps)
         ws = self._ws_async(out_cap)
-        with torch.cuda.device(self.device):
-            check(lib().tvz_catalog_match_gather_async(self._handle, ws.handle, q.ctypes.data, q.shape[0], int(min_match),
-                                                       int(n_peers), int(peer_record.shape[0]), peer_record.ctypes.data,
-                                                       int(my_slots_ptr), int(slot_stride_ints), int(out_cap),
-                                                       int(epoch) & 0xffffffff, self._stream(stream)))
+        check(lib().tvz_catalog_match_gather_async(self._handle, ws.handle, _ptr(q), q.shape[0], int(min_match),
+                                                   int(n_peers), peer_record.shape[0], _ptr(peer_record),
+                                                   my_slots_ptr, slot_stride_ints, out_cap,
+                                                   int(epoch) & 0xffffffff, self._stream(stream)))
 
     def match_batch_gather_async(self, queries, min_match: int, n_peers: int, peer_record: np.ndarray, my_slots_ptr: int,
                                  slot_stride_ints: int, out_cap: int, epoch: int, stream=None) -> None:

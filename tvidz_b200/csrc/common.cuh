@@ -75,6 +75,21 @@ int guarded(F &&body) noexcept {
     }
 }
 
+// Entry points run on the device their catalogue lives on, whatever device the calling thread has current
+// (and leave the caller's choice as it was): bindings need no device context manager around a call.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess) prev = cur;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 #define TVZ_CUDA(expr)                                                                        \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \

@@ -108,7 +108,7 @@ struct alignas(16) TileDesc {
 // TVZ_Q1_WIDE = 1: the single-query kernel runs ONE 1024-thread CTA per SM on a PAIR of adjacent tiles (half the
 // CTAs in the tile-total exchange, one byte map per SM to zero instead of two); 0: one 512-thread CTA per tile, 2 per SM.
 #ifndef TVZ_Q1_WIDE
-#define TVZ_Q1_WIDE 0
+#define TVZ_Q1_WIDE 1   // measured (r02): 1M rows 34.1 vs 37.1 us back to back, 44.6 vs 46.6 us cold; 125k-row shard 20.5 vs 25.1 us cold
 #endif
 template <int kQ>
 struct TileShape {
@@ -1030,6 +1030,7 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
                   int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr) {
     TVZ_REQUIRE(cat && ws && ws->cat == cat, "workspace does not belong to this catalogue");
     TVZ_REQUIRE(qn >= 0 && (qn == 0 || h_q), "bad query");
+    DeviceGuard on_device(cat->device);
     if (!d_out) {
         d_out = ws->d_out;
         if (out_cap <= 0) out_cap = ws->cap;
@@ -1137,6 +1138,7 @@ int ensure_batch_buffers(tvz_match_ws *ws) {
 int enqueue_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all, const int64_t *q_off, int g0, int nb,
                   int min_match, int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr) {
     TVZ_REQUIRE(nb >= 1 && nb <= kBatch, "a batch holds 1..%d queries", kBatch);
+    DeviceGuard on_device(cat->device);
     int rc = ensure_batch_buffers(ws);
     if (rc) return rc;
     if (!d_out) {
@@ -1471,6 +1473,7 @@ int tvz_catalog_upsert(tvz_catalog *c, int32_t video_id, const double *h_ts, int
     return guarded([&]() -> int {
     TVZ_REQUIRE(c && n >= 0 && (n == 0 || h_ts), "bad arguments");
     TVZ_REQUIRE(c->tail_index >= 0, "this catalogue was created immutable (tvz_catalog_create_mutable)");
+    DeviceGuard on_device(c->device);
     std::vector<unsigned long long> vals;
     std::unordered_set<unsigned long long> seen;
     canon_row(h_ts, n, vals, seen);
@@ -1741,6 +1744,8 @@ int tvz_catalog_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *q,
     TVZ_REQUIRE(n_out, "null n_out");
     *n_out = 0;
     TVZ_REQUIRE(cap >= 0 && (cap == 0 || (out_video_id && out_count)), "bad output buffers");
+    TVZ_REQUIRE(cat, "null catalogue");
+    DeviceGuard on_device(cat->device);
     int rc = enqueue_match(cat, ws, q, qn, min_match, out_kth != nullptr, nullptr, 0, ws ? ws->stream : nullptr);
     if (rc) return rc;
     cudaStream_t st = ws->stream;
@@ -1834,6 +1839,7 @@ int tvz_catalog_match_batch(const tvz_catalog *cat, tvz_match_ws *ws, const doub
     TVZ_REQUIRE(cap_total >= 0 && (cap_total == 0 || (out_video_id && out_count)), "bad output buffers");
     out_off[0] = 0;
     if (n_queries == 0) return TVZ_OK;
+    DeviceGuard on_device(cat->device);
     cudaStream_t st = ws->stream;
     const long long rec = (ws->cap + 1) * 2;
     long long written = 0;
