@@ -14,7 +14,13 @@
  * bare `apt-get install ffmpeg`).  No ffmpeg binary or source exists in this
  * image and the reference's tests hold no scene-score vector,
  * so this file restates the published algorithm and is
- * pinned only by the known-answer tests of Appendix A.5 in tests/.
+ * pinned by the known-answer tests of Appendix A.5 in tests/ -- plus, for the
+ * three pieces that live in libavutil, by the REAL library (FFmpeg 8.0.1's
+ * libavutil 60.8, bundled with the image's OpenCV wheel): the pts_time text
+ * against av_ts_make_time_string2, the gt(scene,T) verdict against
+ * av_expr_parse_and_eval, byte-SADs against av_pixelutils block SADs
+ * (tests/test_ffmpeg_libs.py).  get_scene_score itself (mafd, |d mafd|, the
+ * float clip) has no reference-derived vector: for it parity stays unpinned.
  *
  * Each function names the upstream routine it follows.
  */
