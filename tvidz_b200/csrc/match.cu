@@ -1479,7 +1479,8 @@ int tvz_catalog_upsert(tvz_catalog *c, int32_t video_id, const double *h_ts, int
     canon_row(h_ts, n, vals, seen);
     const int nv = static_cast<int>(vals.size());
     std::lock_guard<std::mutex> lk(c->mu);
-    TVZ_REQUIRE(nv <= c->tail_cap_vals, "a row of %d values does not fit the tail (%lld)", nv, c->tail_cap_vals);
+    if (nv > c->tail_cap_vals)
+        return set_error(TVZ_ERR_OVERFLOW, "a row of %d values does not fit the tail (%lld): repack", nv, c->tail_cap_vals);
     if (!c->row_map_built) {   // first upsert: index the packed rows by video id (first row wins, db.py:47)
         std::vector<int> vid(static_cast<size_t>(c->n_rows_main));
         if (c->n_rows_main) TVZ_CUDA(cudaMemcpy(vid.data(), c->d_vid, vid.size() * 4, cudaMemcpyDeviceToHost));
