@@ -202,7 +202,10 @@ int tvz_catalog_match_batch(const tvz_catalog *cat, tvz_match_ws *ws, const doub
  */
 int tvz_catalog_match_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, int qn,
                             int min_match, int32_t *d_out, int64_t out_cap, void *stream);
-/* ... and up to 8 queries at once: d_out is int32 [n_queries][out_cap + 1][2]. */
+/* ... and up to 8 queries at once, answered by ONE kernel launch and one pass over the catalogue: d_out is
+ * int32 [n_queries][out_cap + 1][2].  Each query: <= tvz_catalog_batch_limit() distinct values and <= 65535
+ * values in all; the keys of all 8 travel in the kernel parameters (no copy in front of the launch), q_all is
+ * consumed before the call returns. */
 int tvz_catalog_match_batch_async(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
                                   const int64_t *q_off, int n_queries, int min_match, int32_t *d_out,
                                   int64_t out_cap, void *stream);

@@ -410,3 +410,43 @@ def test_pipelined_async_queries_keep_their_own_results(cuda):
         assert r[0, 1] == 0
         assert [tuple(x) for x in r[1:1 + n].tolist()] == oracle.find_duplicates_csr(ts, off, vid, q, 2)
     cat.close()
+
+
+def test_batches_in_both_parameter_block_sizes(cuda):
+    """A batch's keys ride in the kernel parameters: 96 distinct values per query in the small block, up to 224
+    in the large one; one long query moves the whole batch to the large block; 225 leaves the batch."""
+    ts, off, vid = synth.synth_catalogue(60_000, seed=41)
+    cat = Catalogue(ts, off, vid, hit_capacity=1 << 14)
+    pool = np.unique(ts)
+    rng = np.random.default_rng(41)
+    pick = lambda k: pool[rng.choice(pool.shape[0], k, replace=False)]
+    for sizes in ([96] * 8, [97] + [10] * 7, [224] * 8, [1, 96, 97, 223, 224, 0, 50, 150], [225, 224, 3]):
+        qs = [np.concatenate([pick(k), pick(k)[:k // 3]]) if k else np.zeros(0) for k in sizes]   # some repeats on top
+        qs = [np.concatenate([q, q[:5]]) for q in qs]                                           # ... and exact duplicates
+        assert cat.find_duplicates_many(qs, 2) == [oracle.find_duplicates_csr(ts, off, vid, q, 2) for q in qs], sizes
+    cat.close()
+
+
+def test_exchange_words_survive_the_sequence_wrap(cuda):
+    """Tile totals are exchanged as {16-bit query sequence, total}.  A batch of 8 leaves words for slots 1..7 that
+    single queries never rewrite; 65535 queries later the sequence comes round again and those words must not
+    look current (the state is reset when the sequence wraps)."""
+    import torch
+    ts, off, vid = synth.synth_catalogue(20_001, seed=43)
+    cat = Catalogue(ts, off, vid, hit_capacity=1 << 12)
+    rng = np.random.default_rng(43)
+    qa = [ts[off[r]:off[r + 1]].copy() for r in rng.integers(0, 20_001, 8)]
+    qb = [ts[off[r]:off[r + 1]].copy() for r in rng.integers(0, 20_001, 8)]
+    rec8 = torch.zeros((8, (1 << 12) + 1, 2), dtype=torch.int32, device="cuda")
+    rec = torch.zeros(((1 << 12) + 1, 2), dtype=torch.int32, device="cuda")
+    cat.match_batch_async(qa, 1, rec8)                                  # sequence s on the asynchronous workspace
+    q1 = qa[0][:3]
+    for _ in range(65_534):
+        cat.match_async(q1, 5, rec)
+    cat.match_batch_async(qb, 1, rec8)                                  # sequence s again
+    torch.cuda.synchronize()
+    host = rec8.cpu().numpy()
+    for b, q in enumerate(qb):
+        n = int(host[b, 0, 0])
+        assert [tuple(x) for x in host[b, 1:1 + n].tolist()] == oracle.find_duplicates_csr(ts, off, vid, q, 1)
+    cat.close()

@@ -66,11 +66,21 @@ __host__ __device__ __forceinline__ uint32_t filter_hash(unsigned long long v) {
     return (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> 16;
 }
 
-// Short queries (the common case: a video has tens of cuts) ride in the kernel parameters,
-// which saves the host->device copy in front of the launch.
-struct SmallQuery {
-    unsigned long long keys[kParamKeys];
-    int mult[kParamKeys];
+// Short queries (the common case: a video has tens of cuts) ride in the kernel parameters, which saves the
+// host->device copy in front of the launch -- and with it the copy engine between two kernels of a stream, which
+// would also end the launch overlap (PDL) of consecutive queries.  kP = distinct values per query the parameter block
+// holds; 0 = the keys are in global memory (a long single query).  A batch of 8 comes in two sizes: kBatchShortKeys for
+// ordinary cut lists (9 KB of parameters), kParamKeys (21 KB; the limit is 32,764 bytes) for everything batchable.
+constexpr int kBatchShortKeys = 96;
+template <int kQ, int kP>
+struct QueryParam {
+    unsigned long long keys[kQ][kP];
+    int mult[kQ][kP];
+    int n_keys[kQ];
+};
+template <int kQ>
+struct QueryParam<kQ, 0> {
+    int unused;
 };
 
 // 256-bit streaming load (sm_100 LDG.E.256): no L1 allocation -- shared memory takes ~205 of the SM's
@@ -110,9 +120,18 @@ struct alignas(16) TileDesc {
 #ifndef TVZ_Q1_WIDE
 #define TVZ_Q1_WIDE 1   // measured (r02): 1M rows 34.1 vs 37.1 us back to back, 44.6 vs 46.6 us cold; 125k-row shard 20.5 vs 25.1 us cold
 #endif
+// TVZ_BATCH_WIDE = 1: the 8-query kernel works on tile pairs as well (148 CTAs = ONE wave instead of two: its 128 KB of
+// 16-bit counts + the 64 KB byte map leave room for one CTA per SM either way); 0: one tile per CTA.
+#ifndef TVZ_BATCH_WIDE
+#define TVZ_BATCH_WIDE 1
+#endif
+// TVZ_BATCH_PARAMS = 1: a batch's keys ride in the kernel parameters; 0: staged through pinned memory + one copy.
+#ifndef TVZ_BATCH_PARAMS
+#define TVZ_BATCH_PARAMS 1
+#endif
 template <int kQ>
 struct TileShape {
-    static constexpr int kPair = (kQ == 1 && TVZ_Q1_WIDE) ? 2 : 1;   // adjacent tiles one CTA works on
+    static constexpr int kPair = ((kQ == 1 && TVZ_Q1_WIDE) || (kQ > 1 && TVZ_BATCH_WIDE)) ? 2 : 1;   // adjacent tiles one CTA works on
     static constexpr int kThreads = (kQ == 1 && !TVZ_Q1_WIDE) ? 512 : 1024;
     static constexpr int kMinBlocks = (kQ == 1 && !TVZ_Q1_WIDE) ? 2 : 1;
     static constexpr int kWarps = kThreads / 32;
@@ -258,10 +277,12 @@ __device__ __forceinline__ int lower_bound_u64(const T &at, int n, unsigned long
     return lo;
 }
 
-template <int kQ, bool kParamQuery>
+template <int kQ, int kP>
 __global__ void __launch_bounds__(TileShape<kQ>::kThreads, TileShape<kQ>::kMinBlocks)
-match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ SmallQuery sq) {
+match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ QueryParam<kQ, kP> sq) {
     using S = TileShape<kQ>;
+    constexpr bool kParamQuery = kP > 0;
+    static_assert(kP <= S::kKeys, "the parameter block cannot hold more keys than shared memory does");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem<kQ> &sm = *reinterpret_cast<TileSmem<kQ> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -323,25 +344,41 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
             if (g < unit_hi) v[j] = ld_stream_u32x8(lane_fp + static_cast<size_t>(g) * kFpPerUnit);
         }
     }
-    if (kQ > 1 && tid < kQ) sm.n_keys[tid] = tid < nq ? min(a.n_keys_g[tid], S::kKeys) : 0;
+    if constexpr (kQ > 1) {
+        if (tid < kQ) {
+            int nk = 0;
+            if (tid < nq) {
+                if constexpr (kParamQuery) nk = min(sq.n_keys[tid], kP);
+                else nk = min(a.n_keys_g[tid], S::kKeys);
+            }
+            sm.n_keys[tid] = nk;
+        }
+    }
     __syncthreads();
     mark(2);
-    if (kQ == 1) {
+    if constexpr (kQ == 1) {
         for (int i = tid; i < a.n_keys; i += S::kThreads) {
-            const unsigned long long k = kParamQuery ? sq.keys[i] : a.keys_g[i];
+            unsigned long long k;
+            int m;
+            if constexpr (kParamQuery) { k = sq.keys[0][i]; m = sq.mult[0][i]; }
+            else { k = a.keys_g[i]; m = resident ? a.mult_g[i] : 0; }
             if (resident) {
                 sm.keys[0][i] = k;
-                sm.mult[0][i] = kParamQuery ? sq.mult[i] : a.mult_g[i];
+                sm.mult[0][i] = m;
             }
             sm.map[filter_hash(k)] = 1;
         }
     } else {
-        for (int i = tid; i < nq * a.key_stride; i += S::kThreads) {
-            const int b = i / a.key_stride, k = i - b * a.key_stride;
+        const int stride = kParamQuery ? kP : a.key_stride;
+        for (int i = tid; i < nq * stride; i += S::kThreads) {
+            const int b = i / stride, k = i - b * stride;
             if (k < sm.n_keys[b]) {
-                const unsigned long long key = a.keys_g[i];
+                unsigned long long key;
+                int m;
+                if constexpr (kParamQuery) { key = sq.keys[b][k]; m = sq.mult[b][k]; }
+                else { key = a.keys_g[i]; m = a.mult_g[i]; }
                 sm.keys[b][k] = key;
-                sm.mult[b][k] = a.mult_g[i];
+                sm.mult[b][k] = m;
                 const uint32_t h = filter_hash(key);   // byte-wide OR through the containing 32-bit word
                 atomicOr(reinterpret_cast<unsigned *>(sm.map) + (h >> 2), (1u << b) << (8 * (h & 3)));
             }
@@ -384,8 +421,8 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
                 const int nk = sm.n_keys[b];
                 const int lo = lower_bound_u64([&](int i) { return sm.keys[b][i]; }, nk, val);
                 if (lo >= nk || sm.keys[b][lo] != val) continue;       // filter false positive for this query
-                TVZ_CHECK(b < kQ && local < static_cast<unsigned>(kTileRows));
-                atomicAdd(&sm.counts[b * (kTileRows / 2) + (local >> 1)],
+                TVZ_CHECK(b < kQ && local < static_cast<unsigned>(S::kRows));
+                atomicAdd(&sm.counts[b * (S::kRows / 2) + (local >> 1)],
                           static_cast<unsigned>(sm.mult[b][lo]) << (16 * (local & 1)));
             }
         }
@@ -448,7 +485,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
     const bool want_all = a.min_match <= 0;   // then rows without any match qualify too -- except replaced ones
     auto count_of = [&](int b, int local) -> int {
         if (kQ == 1) return static_cast<int>(sm.counts[local]);
-        return static_cast<int>((sm.counts[b * (kTileRows / 2) + (local >> 1)] >> (16 * (local & 1))) & 0xffffu);
+        return static_cast<int>((sm.counts[b * (S::kRows / 2) + (local >> 1)] >> (16 * (local & 1))) & 0xffffu);
     };
     auto qualifies = [&](int c, int local) -> bool {
         if (local >= td.n_rows || c < a.min_match) return false;
@@ -478,7 +515,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Sm
             if (lane >= o) incl += n;
         }
         if (lane < S::kWarps) sm.warp_tot[b][lane] = incl - w;
-        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);   // <= kTileRows: fits 16 bits
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);   // <= S::kRows <= 8192: fits 16 bits
         if (lane == 0) {
             sm.agg[b] = total;
             st_relaxed_u32(&a.state[static_cast<size_t>(tile) * kQ + b], (a.seq << 16) | total);
@@ -732,6 +769,7 @@ struct tvz_match_ws {
     unsigned *d_state = nullptr;            // [tiles][kBatch] {query sequence << 16 | qualifying rows of the tile}
     unsigned *d_ctrl = nullptr;             // {finished CTAs}: fused gather, zero between queries
     unsigned seq = 0;                       // sequence number of the last query enqueued (1..65535, 0 = none yet)
+    bool wrapped_once = false;              // the sequence has been through 65535 at least once
     int *d_out = nullptr;                   // [cap+1][2]
     long long *d_rows = nullptr;            // [cap]
     int *d_kth = nullptr;                   // [cap]
@@ -949,9 +987,11 @@ int ensure_query_capacity(tvz_match_ws *ws, int qn) {
     return TVZ_OK;
 }
 
-template <int kQ, bool kParam>
+static_assert(sizeof(TileSmem<1>) <= 227 * 1024 && sizeof(TileSmem<kBatch>) <= 227 * 1024, "a CTA has 227 KB of shared memory");
+static_assert(sizeof(TileArgs) + sizeof(QueryParam<kBatch, kParamKeys>) <= 32764, "kernel parameters are limited to 32,764 bytes");
+template <int kQ, int kP>
 cudaError_t set_tile_attr() {
-    return cudaFuncSetAttribute(match_tile_kernel<kQ, kParam>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(match_tile_kernel<kQ, kP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(sizeof(TileSmem<kQ>)));
 }
 // Function attributes are set once per device, not per launch.
@@ -962,9 +1002,14 @@ int ensure_kernel_attrs() {
     TVZ_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(mu);
     if (dev >= 0 && dev < 64 && done[dev]) return TVZ_OK;
-    TVZ_CUDA((set_tile_attr<1, true>()));
-    TVZ_CUDA((set_tile_attr<1, false>()));
-    TVZ_CUDA((set_tile_attr<kBatch, false>()));
+    TVZ_CUDA((set_tile_attr<1, kParamKeys>()));
+    TVZ_CUDA((set_tile_attr<1, 0>()));
+#if TVZ_BATCH_PARAMS
+    TVZ_CUDA((set_tile_attr<kBatch, kBatchShortKeys>()));
+    TVZ_CUDA((set_tile_attr<kBatch, kParamKeys>()));
+#else
+    TVZ_CUDA((set_tile_attr<kBatch, 0>()));
+#endif
     if (dev >= 0 && dev < 64) done[dev] = true;
     return TVZ_OK;
 }
@@ -1006,6 +1051,19 @@ void base_args(const tvz_catalog *cat, tvz_match_ws *ws, const CatView &cv, Tile
     a.trace = ws->d_trace;
     ws->seq = ws->seq >= 0xffffu ? 1u : ws->seq + 1u;   // never 0: that is what fresh state[] entries carry
     a.seq = ws->seq;
+}
+
+// The 16-bit sequence has wrapped: an exchange entry that no query has rewritten for a whole cycle (slot b of a
+// tile, after 65535 queries none of which was a batch with more than b queries) would look current again, so
+// every entry goes back to "fresh" first.  Stream-ordered in front of the query that carries sequence 1.
+int reset_state_on_wrap(const tvz_catalog *cat, tvz_match_ws *ws, cudaStream_t st) {
+    if (ws->seq != 1u || !ws->wrapped_once) {
+        ws->wrapped_once = ws->wrapped_once || ws->seq == 0xffffu;
+        return TVZ_OK;
+    }
+    const size_t n_state = static_cast<size_t>(std::max<long long>(1, cat->max_tiles())) * kBatch;
+    TVZ_CUDA(cudaMemsetAsync(ws->d_state, 0, n_state * 4, st));
+    return TVZ_OK;
 }
 
 // A query must see every upsert that returned before it was enqueued.  (Also: tiles that appear for the
@@ -1079,6 +1137,8 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
         if (rc) return rc;
         TileArgs a{};
         base_args(cat, ws, cv, a);
+        rc = reset_state_on_wrap(cat, ws, st);
+        if (rc) return rc;
         a.n_queries = 1;
         a.n_keys = nk;
         a.min_match = min_match;
@@ -1098,12 +1158,13 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
         const dim3 grid(static_cast<unsigned>((cv.n_tiles + TileShape<1>::kPair - 1) / TileShape<1>::kPair)), block(TileShape<1>::kThreads);
         if (param) {
-            SmallQuery sq;
-            memcpy(sq.keys, h_keys, sizeof(unsigned long long) * nk);
-            memcpy(sq.mult, h_mult, sizeof(int) * nk);
-            TVZ_CUDA(launch_pdl(match_tile_kernel<1, true>, grid, block, sizeof(TileSmem<1>), st, a, sq));
+            QueryParam<1, kParamKeys> sq;
+            memcpy(sq.keys[0], h_keys, sizeof(unsigned long long) * nk);
+            memcpy(sq.mult[0], h_mult, sizeof(int) * nk);
+            sq.n_keys[0] = nk;
+            TVZ_CUDA(launch_pdl(match_tile_kernel<1, kParamKeys>, grid, block, sizeof(TileSmem<1>), st, a, sq));
         } else {
-            TVZ_CUDA(launch_pdl(match_tile_kernel<1, false>, grid, block, sizeof(TileSmem<1>), st, a, SmallQuery{}));
+            TVZ_CUDA(launch_pdl(match_tile_kernel<1, 0>, grid, block, sizeof(TileSmem<1>), st, a, QueryParam<1, 0>{}));
         }
         if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
         if (want_kth) {
@@ -1124,17 +1185,69 @@ int enqueue_match(const tvz_catalog *cat, tvz_match_ws *ws, const double *h_q, i
 }
 
 int ensure_batch_buffers(tvz_match_ws *ws) {
-    if (ws->b_dev) return TVZ_OK;
+    if (ws->b_out) return TVZ_OK;
     TVZ_CUDA(cudaMalloc(&ws->b_out, kBatch * (ws->cap + 1) * 8));
+    TVZ_CUDA(cudaHostAlloc(&ws->hb_out, kBatch * (ws->cap + 1) * 8, cudaHostAllocDefault));
+#if !TVZ_BATCH_PARAMS
     TVZ_CUDA(cudaMalloc(&ws->b_dev, kBatchStageBytes));
     TVZ_CUDA(cudaHostAlloc(&ws->hb_stage, kStageSlots * kBatchStageBytes, cudaHostAllocDefault));
-    TVZ_CUDA(cudaHostAlloc(&ws->hb_out, kBatch * (ws->cap + 1) * 8, cudaHostAllocDefault));
     for (int i = 0; i < kStageSlots; ++i) TVZ_CUDA(cudaEventCreateWithFlags(&ws->b_staged[i], cudaEventDisableTiming));
+#endif
     return TVZ_OK;
 }
 
-// Up to kBatch queries in one pass: keys staged with ONE copy, one kernel; records land in
-// d_out [nb][out_stride] (NULL: the workspace's own b_out with out_stride = 2 * (cap + 1)).
+// Sorted distinct values (canonical bit patterns) and multiplicities of query g0 + b into keys / mult [stride];
+// -> number of distinct values.
+int batch_query_keys(const double *q_all, const int64_t *q_off, int g, std::vector<unsigned long long> &sorted,
+                     unsigned long long *keys, int *mult, int limit, int *nk_out) {
+    const double *q = q_all + q_off[g];
+    const long long qn = q_off[g + 1] - q_off[g];
+    TVZ_REQUIRE(qn >= 0, "query offsets must be non-decreasing");
+    TVZ_REQUIRE(qn <= 65535, "query %d has %lld values: not batchable (16-bit counts)", g, qn);
+    sorted.clear();
+    bool ascending = true;
+    for (long long i = 0; i < qn; ++i) {
+        const unsigned long long bits = canon_bits(q[i]);
+        if (is_nan_bits(bits)) continue;
+        if (!sorted.empty() && bits < sorted.back()) ascending = false;
+        sorted.push_back(bits);
+    }
+    if (!ascending) std::sort(sorted.begin(), sorted.end());   // production queries are ascending cut lists (app.py:231)
+    int nk = 0;
+    for (size_t i = 0; i < sorted.size();) {
+        size_t j = i;
+        while (j < sorted.size() && sorted[j] == sorted[i]) ++j;
+        if (nk < limit) {
+            keys[nk] = sorted[i];
+            mult[nk] = static_cast<int>(j - i);
+        }
+        ++nk;
+        i = j;
+    }
+    *nk_out = nk;
+    return TVZ_OK;
+}
+
+template <int kP>
+int launch_batch_params(const tvz_match_ws *ws, const TileArgs &a, const unsigned long long *keys, const int *mult,
+                        const int *nk, int nb, dim3 grid, cudaStream_t st) {
+    QueryParam<kBatch, kP> qp;
+    for (int b = 0; b < kBatch; ++b) {
+        qp.n_keys[b] = b < nb ? nk[b] : 0;
+        if (b < nb && nk[b] > 0) {
+            memcpy(qp.keys[b], keys + static_cast<size_t>(b) * kParamKeys, sizeof(unsigned long long) * nk[b]);
+            memcpy(qp.mult[b], mult + static_cast<size_t>(b) * kParamKeys, sizeof(int) * nk[b]);
+        }
+    }
+    if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
+    TVZ_CUDA(launch_pdl(match_tile_kernel<kBatch, kP>, grid, dim3(TileShape<kBatch>::kThreads), sizeof(TileSmem<kBatch>), st, a, qp));
+    if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
+    return TVZ_OK;
+}
+
+// Up to kBatch queries in one pass, one kernel; records land in d_out [nb][out_stride] (NULL: the workspace's
+// own b_out with out_stride = 2 * (cap + 1)).  The keys ride in the kernel parameters (TVZ_BATCH_PARAMS; else:
+// staged through pinned memory with ONE copy in front of the kernel).
 int enqueue_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all, const int64_t *q_off, int g0, int nb,
                   int min_match, int *d_out, long long out_cap, cudaStream_t st, const GatherTargets *gather = nullptr) {
     TVZ_REQUIRE(nb >= 1 && nb <= kBatch, "a batch holds 1..%d queries", kBatch);
@@ -1146,6 +1259,15 @@ int enqueue_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
         if (out_cap <= 0) out_cap = ws->cap;
     }
     TVZ_REQUIRE(out_cap >= 1 && out_cap <= ws->cap, "output capacity %lld outside [1, %lld]", out_cap, ws->cap);
+#if TVZ_BATCH_PARAMS
+    // thread-local scratch: concurrent callers have their own workspaces, but why allocate per call
+    static thread_local std::vector<unsigned long long> keys_buf(static_cast<size_t>(kBatch) * kParamKeys);
+    static thread_local std::vector<int> mult_buf(static_cast<size_t>(kBatch) * kParamKeys);
+    unsigned long long *h_keys = keys_buf.data();
+    int *h_mult = mult_buf.data();
+    int nk_arr[kBatch] = {};
+    int *h_nk = nk_arr;
+#else
     const int slot = ws->b_slot;
     ws->b_slot = (slot + 1) % kStageSlots;
     if (ws->b_stage_busy[slot]) { TVZ_CUDA(cudaEventSynchronize(ws->b_staged[slot])); ws->b_stage_busy[slot] = false; }
@@ -1153,30 +1275,16 @@ int enqueue_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
     unsigned long long *h_keys = reinterpret_cast<unsigned long long *>(stage);
     int *h_mult = reinterpret_cast<int *>(stage + kBatchKeysBytes);
     int *h_nk = reinterpret_cast<int *>(stage + kBatchKeysBytes + kBatchMultBytes);
-    std::vector<unsigned long long> sorted;
     for (int b = 0; b < kBatch; ++b) h_nk[b] = 0;
+#endif
+    static thread_local std::vector<unsigned long long> sorted;
+    int nk_max = 0;
     for (int b = 0; b < nb; ++b) {
-        const double *q = q_all + q_off[g0 + b];
-        const long long qn = q_off[g0 + b + 1] - q_off[g0 + b];
-        TVZ_REQUIRE(qn >= 0, "query offsets must be non-decreasing");
-        TVZ_REQUIRE(qn <= 65535, "query %d has %lld values: not batchable (16-bit counts)", g0 + b, qn);
-        sorted.clear();
-        for (long long i = 0; i < qn; ++i) {
-            const unsigned long long bits = canon_bits(q[i]);
-            if (!is_nan_bits(bits)) sorted.push_back(bits);
-        }
-        std::sort(sorted.begin(), sorted.end());
-        int nk = 0;
-        for (size_t i = 0; i < sorted.size();) {
-            size_t j = i;
-            while (j < sorted.size() && sorted[j] == sorted[i]) ++j;
-            TVZ_REQUIRE(nk < kParamKeys, "query %d has more than %d distinct values: not batchable", g0 + b, kParamKeys);
-            h_keys[b * kParamKeys + nk] = sorted[i];
-            h_mult[b * kParamKeys + nk] = static_cast<int>(j - i);
-            ++nk;
-            i = j;
-        }
-        h_nk[b] = nk;
+        rc = batch_query_keys(q_all, q_off, g0 + b, sorted, h_keys + static_cast<size_t>(b) * kParamKeys,
+                              h_mult + static_cast<size_t>(b) * kParamKeys, kParamKeys, &h_nk[b]);
+        if (rc) return rc;
+        TVZ_REQUIRE(h_nk[b] <= kParamKeys, "query %d has more than %d distinct values: not batchable", g0 + b, kParamKeys);
+        nk_max = std::max(nk_max, h_nk[b]);
     }
     const CatView cv = view_of(cat);
     rc = wait_for_mutations(cat, ws, cv, st);
@@ -1189,14 +1297,10 @@ int enqueue_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
     }
     rc = ensure_kernel_attrs();
     if (rc) return rc;
-    TVZ_CUDA(cudaMemcpyAsync(ws->b_dev, stage, kBatchStageBytes, cudaMemcpyHostToDevice, st));
-    TVZ_CUDA(cudaEventRecord(ws->b_staged[slot], st));
-    ws->b_stage_busy[slot] = true;
     TileArgs a{};
     base_args(cat, ws, cv, a);
-    a.keys_g = reinterpret_cast<const unsigned long long *>(ws->b_dev);
-    a.mult_g = reinterpret_cast<const int *>(ws->b_dev + kBatchKeysBytes);
-    a.n_keys_g = reinterpret_cast<const int *>(ws->b_dev + kBatchKeysBytes + kBatchMultBytes);
+    rc = reset_state_on_wrap(cat, ws, st);
+    if (rc) return rc;
     a.key_stride = kParamKeys;
     a.n_queries = nb;
     a.min_match = min_match;
@@ -1208,11 +1312,23 @@ int enqueue_batch(const tvz_catalog *cat, tvz_match_ws *ws, const double *q_all,
         a.gt = *gather;
         a.gt.query_stride = 4 * (out_cap + 1);   // tagged entries are 4 ints
     }
+    const dim3 grid(static_cast<unsigned>((cv.n_tiles + TileShape<kBatch>::kPair - 1) / TileShape<kBatch>::kPair));
+#if TVZ_BATCH_PARAMS
+    if (nk_max <= kBatchShortKeys) return launch_batch_params<kBatchShortKeys>(ws, a, h_keys, h_mult, h_nk, nb, grid, st);
+    return launch_batch_params<kParamKeys>(ws, a, h_keys, h_mult, h_nk, nb, grid, st);
+#else
+    TVZ_CUDA(cudaMemcpyAsync(ws->b_dev, stage, kBatchStageBytes, cudaMemcpyHostToDevice, st));
+    TVZ_CUDA(cudaEventRecord(ws->b_staged[slot], st));
+    ws->b_stage_busy[slot] = true;
+    a.keys_g = reinterpret_cast<const unsigned long long *>(ws->b_dev);
+    a.mult_g = reinterpret_cast<const int *>(ws->b_dev + kBatchKeysBytes);
+    a.n_keys_g = reinterpret_cast<const int *>(ws->b_dev + kBatchKeysBytes + kBatchMultBytes);
     if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t0, st));
-    TVZ_CUDA(launch_pdl(match_tile_kernel<kBatch, false>, dim3(static_cast<unsigned>(cv.n_tiles)),
-                        dim3(TileShape<kBatch>::kThreads), sizeof(TileSmem<kBatch>), st, a, SmallQuery{}));
+    TVZ_CUDA(launch_pdl(match_tile_kernel<kBatch, 0>, grid, dim3(TileShape<kBatch>::kThreads), sizeof(TileSmem<kBatch>), st,
+                        a, QueryParam<kBatch, 0>{}));
     if (ws->timing) TVZ_CUDA(cudaEventRecord(ws->t1, st));
     return TVZ_OK;
+#endif
 }
 
 int make_gather(int n_peers, int n_dst, const uint64_t *peer_record, const int32_t *d_my_slots, int64_t slot_stride_ints,
