@@ -53,6 +53,7 @@ constexpr int kTileRows = 4096;              // rows whose counts one CTA keeps 
 constexpr int kTileKeys = 1024;              // distinct values of ONE query kept in shared memory (more: searched in global memory)
 constexpr int kParamKeys = 224;              // distinct values that ride in the kernel parameters; per-query limit of a batch
 constexpr int kBatch = 8;                    // queries per batched pass
+constexpr int kRecvCtas = 32;                // fused gather: CTAs (the grid's last) that wait for the peers' records
 constexpr int kMinTileUnits = 32;            // small catalogues: at least two units per warp and tile
 constexpr int kFpPadUnits = 64;              // fingerprint array padding: a tile's first (speculative) loads stay in bounds
 constexpr int kMaxTailTiles = 16;            // the mutable tail: up to 16 tiles = 65536 rows between repacks
@@ -128,6 +129,11 @@ struct alignas(16) TileDesc {
 // TVZ_BATCH_PARAMS = 1: a batch's keys ride in the kernel parameters; 0: staged through pinned memory + one copy.
 #ifndef TVZ_BATCH_PARAMS
 #define TVZ_BATCH_PARAMS 1
+#endif
+// TVZ_STAGED_EMIT = 1: a CTA's hits are ordered in shared memory first and written out by consecutive threads
+// (coalesced record stores, contiguous NVLink stores in the fused gather); 0: every thread stores its own hits.
+#ifndef TVZ_STAGED_EMIT
+#define TVZ_STAGED_EMIT 1
 #endif
 template <int kQ>
 struct TileShape {
@@ -564,6 +570,55 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Qu
         }
         __syncthreads();
         mark(9);
+#if TVZ_STAGED_EMIT
+        // The hits go through shared memory -- the byte map's 64 KB are free once the stream has ended -- so that
+        // consecutive threads write consecutive entries: a warp's stores to the record (and, fused gather, its tagged
+        // 16-byte stores to the peers) cover contiguous 256 (512) bytes instead of 32 scattered entries.
+        int2 *stage = reinterpret_cast<int2 *>(sm.map);
+        static_assert(S::kRows * sizeof(int2) <= kMapEntries, "the staging area is the byte map");
+        for (int b = 0; b < nq; ++b) {
+            int cnt[S::kRowsPerThread];
+            int mine = 0;
+#pragma unroll
+            for (int j = 0; j < S::kRowsPerThread; ++j) {
+                cnt[j] = count_of(b, r0 + j);
+                if (qualifies(cnt[j], r0 + j)) ++mine; else cnt[j] = -1;   // counts are never negative
+            }
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const long long base = static_cast<long long>(sm.excl[b]);
+            int lpos = static_cast<int>(sm.warp_tot[b][warp]) + (incl - mine);   // rank of the thread's first hit within the CTA
+#pragma unroll
+            for (int j = 0; j < S::kRowsPerThread; ++j) {
+                if (cnt[j] >= 0) {
+                    const int row = td.row_lo + r0 + j;
+                    TVZ_CHECK(row < a.n_rows_cap && r0 + j < td.n_rows && lpos >= 0 && lpos < S::kRows);
+                    stage[lpos] = make_int2(a.vid[row], cnt[j]);
+                    if (kQ == 1 && a.rows_out && base + lpos < a.cap) a.rows_out[base + lpos] = row;
+                    ++lpos;
+                }
+            }
+            __syncthreads();
+            const int total = static_cast<int>(sm.agg[b]);
+            int *o = a.out + b * a.out_stride;
+            for (int i = tid; i < total; i += S::kThreads) {
+                const long long pos = base + i;
+                if (pos < a.cap) {
+                    const int2 hit = stage[i];
+                    *reinterpret_cast<int2 *>(o + 2 + 2 * pos) = hit;
+                    // fused gather: every CTA ships its own hits to all peers as it places them (NVLink stores, in
+                    // parallel across CTAs), each 8-byte half tagged with the query epoch
+                    for (int p = 0; p < a.gt.n_dst; ++p)
+                        st_tagged(a.gt.record[p] + b * a.gt.query_stride + 4 * (1 + pos), hit, a.gt.epoch);
+                }
+            }
+            if (b + 1 < nq) __syncthreads();   // the next query's hits reuse the staging area
+        }
+#else
         for (int b = 0; b < nq; ++b) {
             int cnt[S::kRowsPerThread];
             int mine = 0;
@@ -599,6 +654,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Qu
                 }
             }
         }
+#endif
     }   // !idle
     mark(10);
 
@@ -607,31 +663,64 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Qu
     // {value0, epoch, value1, epoch} -- entry 0 = {n_hits, overflow}, entry 1 + h = {video_id, match_count} -- and
     // each 8-byte half is stored atomically, so a reader that sees the epoch in both halves has the data.  Senders
     // therefore need no system-scope fence, no done-counter and no flag: CTAs just store and exit.  The receivers
-    // are the LAST n_peers CTAs of the grid, one peer each: the whole CTA polls the header of that peer's slot in
-    // this rank's OWN memory, then sweeps the hit entries (four independent 16-byte loads per thread and round; an
-    // entry that is not there yet is polled, bounded).  When the kernel completes, all records are complete here.
+    // are the LAST kRecvCtas CTAs of the grid.  Each polls the headers of all n_peers x n_queries lists in this
+    // rank's OWN memory (one thread per header, side by side), then the lists are swept as ONE index space cut
+    // into equal shares, a share per receiver (four independent 16-byte loads per thread and round; an entry that
+    // is not there yet is polled, bounded) -- so the wait costs two round trips however the hits are spread over
+    // peers and queries (one receiver per peer, the first form, took 17 rounds for 68 k hits per peer at N = 2).
+    // When the kernel completes, all records are complete here.
     if (a.gt.n_peers == 0) return;
     const int back = static_cast<int>(gridDim.x) - 1 - tile;            // 0 for the last CTA
-    const int n_recv = min(static_cast<int>(gridDim.x), a.gt.n_peers);
+    const int n_recv = min(static_cast<int>(gridDim.x), kRecvCtas);
     if (back >= n_recv) return;
     mark(11);
-    for (int p = back; p < a.gt.n_peers; p += n_recv) {
-        for (int b = 0; b < nq; ++b) {
-            const int *slot = a.gt.my_slots + p * a.gt.slot_stride + b * a.gt.query_stride;
-            const int2 hdr = ld_tagged(slot, a.gt.epoch);                   // (every thread polls the header: same address)
-            const long long n = min(static_cast<long long>(hdr.x), a.cap);
-            for (long long i0 = tid; i0 < n; i0 += 4 * S::kThreads) {
-                bool there[4];
+    const int n_lists = a.gt.n_peers * nq;                              // <= kMaxPeers * kBatch
+    long long *first = reinterpret_cast<long long *>(&sm.qe[0][0]);     // [n_lists + 1]; the survivor queues are long done
+    static_assert(sizeof(sm.qe) >= (kMaxPeers * kBatch + 1) * sizeof(long long), "list offsets live in the survivor queues");
+    auto list_slot = [&](int l) -> const int * {
+        const int p = l / nq, b = l - p * nq;
+        return a.gt.my_slots + p * a.gt.slot_stride + b * a.gt.query_stride;
+    };
+    if (tid < n_lists) first[1 + tid] = min(static_cast<long long>(ld_tagged(list_slot(tid), a.gt.epoch).x), a.cap);
+    if (tid == 0) first[0] = 0;
+    __syncthreads();
+    if (warp == 0) {   // lengths -> exclusive offsets
+        long long carry = 0;
+        for (int c = 0; c < n_lists; c += 32) {
+            long long incl = c + lane < n_lists ? first[1 + c + lane] : 0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const long long i = i0 + u * S::kThreads;
-                    there[u] = i >= n || try_tagged(slot + 4 * (1 + i), a.gt.epoch);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (!there[u]) (void)ld_tagged(slot + 4 * (1 + i0 + u * S::kThreads), a.gt.epoch);
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
             }
+            if (c + lane < n_lists) first[1 + c + lane] = carry + incl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
+    }
+    __syncthreads();
+    const long long n_all = first[n_lists];
+    const long long share = (n_all + n_recv - 1) / n_recv;
+    const long long f_lo = back * share, f_hi = min(n_all, f_lo + share);
+    auto entry_of = [&](long long f) -> const int * {   // the list whose range [first[l], first[l + 1]) holds f
+        int l = 0, h = n_lists;
+        while (h - l > 1) {
+            const int mid = (l + h) >> 1;
+            if (first[mid] <= f) l = mid; else h = mid;
+        }
+        return list_slot(l) + 4 * (1 + (f - first[l]));
+    };
+    for (long long f0 = f_lo + tid; f0 < f_hi; f0 += 4 * S::kThreads) {
+        const int *e[4];
+        bool there[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long f = f0 + u * S::kThreads;
+            e[u] = f < f_hi ? entry_of(f) : nullptr;
+            there[u] = !e[u] || try_tagged(e[u], a.gt.epoch);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (!there[u]) (void)ld_tagged(e[u], a.gt.epoch);
     }
     mark(15);
 }
