@@ -130,8 +130,11 @@ struct alignas(16) TileDesc {
 #ifndef TVZ_BATCH_PARAMS
 #define TVZ_BATCH_PARAMS 1
 #endif
-// TVZ_STAGED_EMIT = 1: a CTA's hits are ordered in shared memory first and written out by consecutive threads
-// (coalesced record stores, contiguous NVLink stores in the fused gather); 0: every thread stores its own hits.
+// TVZ_STAGED_EMIT: whose hits are ordered in shared memory first and written out by consecutive threads (coalesced
+// record stores, contiguous NVLink stores in the fused gather) instead of every thread storing its own.
+// 1 = the 8-query pass only (shipped), 2 = single queries too, 0 = nobody.  Measured: 8 queries at 1 M rows 92.0 ->
+// 89.4 us per pass, at N = 2 with the gather 109.2 -> 104.8 us; one query at N = 1 is 0.8 us SLOWER staged (two more
+// barriers for 19 k hits spread over 148 CTAs), at N = 2 the same within noise (profiles/r02_gather_variants_n2.txt).
 #ifndef TVZ_STAGED_EMIT
 #define TVZ_STAGED_EMIT 1
 #endif
@@ -570,7 +573,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Qu
         }
         __syncthreads();
         mark(9);
-#if TVZ_STAGED_EMIT
+        if constexpr (TVZ_STAGED_EMIT == 2 || (TVZ_STAGED_EMIT == 1 && kQ > 1)) {
         // The hits go through shared memory -- the byte map's 64 KB are free once the stream has ended -- so that
         // consecutive threads write consecutive entries: a warp's stores to the record (and, fused gather, its tagged
         // 16-byte stores to the peers) cover contiguous 256 (512) bytes instead of 32 scattered entries.
@@ -618,7 +621,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Qu
             }
             if (b + 1 < nq) __syncthreads();   // the next query's hits reuse the staging area
         }
-#else
+        } else {
         for (int b = 0; b < nq; ++b) {
             int cnt[S::kRowsPerThread];
             int mine = 0;
@@ -654,7 +657,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Qu
                 }
             }
         }
-#endif
+        }
     }   // !idle
     mark(10);
 
