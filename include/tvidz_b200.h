@@ -215,7 +215,7 @@ int tvz_catalog_match_batch_async(const tvz_catalog *cat, tvz_match_ws *ws, cons
  * buffer, in a TAGGED form: entry e of a slot is 16 bytes {value0, epoch, value1, epoch} -- entry 0 =
  * {n_hits, overflow}, entry 1 + h = {video_id, match_count} -- and every 8-byte half is stored
  * atomically, so a reader that finds `epoch` in both halves has the data.  Senders need no
- * system-scope fence, no flag and no counter; the kernel's last CTA polls (bounded) the slots of all
+ * system-scope fence, no flag and no counter; the kernel's last CTAs poll (bounded) the slots of all
  * peers in this rank's OWN buffer until they are complete for `epoch` -- no second kernel, no
  * collective.  When the kernel has completed, every shard's record is in d_my_slots.
  *   peer_record[p] : device address (peer memory) of THIS rank's slot inside peer p's buffer;
