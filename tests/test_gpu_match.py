@@ -450,3 +450,35 @@ def test_exchange_words_survive_the_sequence_wrap(cuda):
         n = int(host[b, 0, 0])
         assert [tuple(x) for x in host[b, 1:1 + n].tolist()] == oracle.find_duplicates_csr(ts, off, vid, q, 1)
     cat.close()
+
+
+def test_fused_gather_loopback_with_eight_peers(cuda):
+    """One GPU plays all 8 ranks of the fused gather: the kernel stores its tagged record into 8 slots of an
+    ordinary device buffer (one "peer" each) and its last CTAs wait for 8 x n_queries lists -- the shape of an
+    8-GPU run (64 lists for a batch), without the 8 GPUs.  Two epochs, so the second one meets stale tags."""
+    import torch
+    ts, off, vid = synth.synth_catalogue(20_001, seed=47)
+    cap = 1 << 12
+    cat = Catalogue(ts, off, vid, hit_capacity=cap)
+    rng = np.random.default_rng(47)
+    world = 8
+    for nq in (1, 8):
+        rec_ints = nq * (cap + 1) * 4
+        buf = torch.zeros(world * rec_ints, dtype=torch.int32, device="cuda")
+        peers = np.asarray([buf.data_ptr() + 4 * p * rec_ints for p in range(world)], np.uint64)
+        for epoch in (1, 2):
+            qs = [ts[off[r]:off[r + 1]].copy() for r in rng.integers(0, 20_001, nq)]
+            if nq == 1:
+                cat.match_gather_async(qs[0], 1, world, peers, buf.data_ptr(), rec_ints, cap, epoch)
+            else:
+                cat.match_batch_gather_async(qs, 1, world, peers, buf.data_ptr(), rec_ints, cap, epoch)
+            torch.cuda.synchronize()
+            host = buf.cpu().numpy().reshape(world, nq, cap + 1, 4)
+            for b, q in enumerate(qs):
+                want = oracle.find_duplicates_csr(ts, off, vid, q, 1)
+                for p in range(world):
+                    n = int(host[p, b, 0, 0])
+                    assert n == len(want) and host[p, b, 0, 2] == 0
+                    assert (host[p, b, :n + 1, 1::2] == epoch).all()
+                    assert [tuple(x) for x in host[p, b, 1:1 + n, 0::2].tolist()] == want
+    cat.close()
