@@ -187,7 +187,6 @@ struct TileArgs {
     long long *rows_out;                    // [cap] row index of every hit (single query; nullable)
     long long *n_hits_out;                  // [n_queries]
     unsigned *state;                        // [n_tiles][kQ]: {query sequence << 16 | qualifying rows of the tile}
-    unsigned *ctrl;                         // {finished CTAs} (fused gather only)
     unsigned seq;                           // this query's sequence number on its workspace (1..65535)
     int uniform_units;                      // > 0: packed tile t starts at unit t * uniform_units (no lookup before the first loads)
     long long *trace;                       // debug: [n_tiles][16] phase timestamps (tvz_debug_tile_trace), normally null
@@ -224,7 +223,8 @@ __device__ __forceinline__ void st_tagged(int *entry, int2 v, unsigned epoch) {
 }
 // One look at an entry: are both halves there?
 __device__ __forceinline__ bool try_tagged(const int *entry, unsigned epoch) {
-    unsigned a0, t0, a1, t1;
+    [[maybe_unused]] unsigned a0, a1;   // the values: only the tags are looked at here
+    unsigned t0, t1;
     asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(t0), "=r"(a1), "=r"(t1) : "l"(entry) : "memory");
     return t0 == epoch && t1 == epoch;
 }
@@ -397,7 +397,7 @@ match_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ Qu
     if (tid * 32 < td.n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vid + td.row_lo + tid * 32));
     __syncthreads();
     mark(3);
-    pdl_wait();               // the previous query on this workspace still owns state / ctrl / out until here
+    pdl_wait();               // the previous query on this workspace still owns state / out until here
     pdl_launch_dependents();  // the next kernel may run its own prologue while this one streams
     mark(4);
 
@@ -859,7 +859,6 @@ struct tvz_match_ws {
     const tvz_catalog *cat = nullptr;
     long long cap = 0;
     unsigned *d_state = nullptr;            // [tiles][kBatch] {query sequence << 16 | qualifying rows of the tile}
-    unsigned *d_ctrl = nullptr;             // {finished CTAs}: fused gather, zero between queries
     unsigned seq = 0;                       // sequence number of the last query enqueued (1..65535, 0 = none yet)
     bool wrapped_once = false;              // the sequence has been through 65535 at least once
     int *d_out = nullptr;                   // [cap+1][2]
@@ -895,10 +894,12 @@ struct tvz_match_ws {
 
 namespace {
 
+#if !TVZ_BATCH_PARAMS   // the staged form of a batch's keys (measurement variant, scripts/batch_variants.sh)
 constexpr size_t kBatchKeysBytes = static_cast<size_t>(kBatch) * kParamKeys * 8;
 constexpr size_t kBatchMultBytes = static_cast<size_t>(kBatch) * kParamKeys * 4;
 constexpr size_t kBatchStageBytes = (kBatchKeysBytes + kBatchMultBytes + kBatch * 4 + 63) / 64 * 64;
 constexpr int kStageSlots = 4;   // pinned staging slots: the host prepares batch k+1..k+3 while batch k still waits for its copy
+#endif
 
 inline unsigned long long canon_bits(double v) {
     unsigned long long b;
@@ -1135,7 +1136,6 @@ void base_args(const tvz_catalog *cat, tvz_match_ws *ws, const CatView &cv, Tile
     a.vid = cat->d_vid;
     a.dead = cat->d_dead;
     a.state = ws->d_state;
-    a.ctrl = ws->d_ctrl;
     a.n_hits_out = ws->d_nhits;
     a.uniform_units = cat->uniform_units;
     a.n_pos = cat->n_pos_all;
@@ -1827,8 +1827,6 @@ int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_
     const size_t n_state = static_cast<size_t>(std::max<long long>(1, cat->max_tiles())) * kBatch;
     if ((e = cudaMalloc(&ws->d_state, n_state * 4)) != cudaSuccess) return bail(e, "cudaMalloc(state)");
     if ((e = cudaMemsetAsync(ws->d_state, 0, n_state * 4, st)) != cudaSuccess) return bail(e, "cudaMemset(state)");
-    if ((e = cudaMalloc(&ws->d_ctrl, 8)) != cudaSuccess) return bail(e, "cudaMalloc(ctrl)");
-    if ((e = cudaMemsetAsync(ws->d_ctrl, 0, 8, st)) != cudaSuccess) return bail(e, "cudaMemset(ctrl)");
     if ((e = cudaMalloc(&ws->d_out, (ws->cap + 1) * 8)) != cudaSuccess) return bail(e, "cudaMalloc(out)");
     if ((e = cudaMemsetAsync(ws->d_out, 0, 8, st)) != cudaSuccess) return bail(e, "cudaMemset(out)");
     if ((e = cudaMalloc(&ws->d_rows, ws->cap * 8)) != cudaSuccess) return bail(e, "cudaMalloc(rows)");
@@ -1853,7 +1851,7 @@ int tvz_match_ws_create(const tvz_catalog *cat, int64_t hit_capacity, tvz_match_
 void tvz_match_ws_destroy(tvz_match_ws *ws) {
     if (!ws) return;
     if (ws->stream) cudaStreamSynchronize(ws->stream);
-    void *dev[] = {ws->d_state, ws->d_ctrl, ws->d_out, ws->d_rows, ws->d_kth, ws->d_nhits, ws->d_qcanon, ws->d_mult,
+    void *dev[] = {ws->d_state, ws->d_out, ws->d_rows, ws->d_kth, ws->d_nhits, ws->d_qcanon, ws->d_mult,
                    ws->b_out, ws->b_dev};
     for (void *p : dev)
         if (p) cudaFree(p);
